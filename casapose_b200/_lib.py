@@ -1,0 +1,136 @@
+"""ctypes binding of libcasapose_b200.so (include/casapose_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, the Python layer raises.
+PyTorch is used only as the carrier of device memory / streams (any ``__dlpack__`` exporter is
+accepted and viewed zero-copy); no torch type crosses the C ABI.
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libcasapose_b200.so")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+STATUS_BITS = {
+    1: "MASK_NOT_BINARY",
+    2: "PIX_OVERFLOW",
+    4: "IDX_RANGE",
+    8: "EMPTY_AFTER_CAP",
+}
+
+
+class CasaError(RuntimeError):
+    pass
+
+
+class RansacParams(C.Structure):
+    _fields_ = [
+        ("b", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("oc", C.c_int32), ("vn", C.c_int32),
+        ("round_hyp_num", C.c_int32), ("max_iter", C.c_int32),
+        ("inlier_thresh", C.c_float), ("confidence", C.c_float), ("min_num", C.c_float), ("max_num", C.c_float),
+        ("seed", C.c_uint64), ("image_offset", C.c_int32), ("pix_capacity", C.c_int32),
+        ("force_exact", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class RansacDebug(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "tn0", "tn", "rounds", "counts", "win_idx", "hyps", "win_pts", "win_ratio",
+        "ata", "atb", "refined", "pix", "pix_off", "stats")]
+
+
+class LsParams(C.Structure):
+    _fields_ = [
+        ("b", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("num_classes", C.c_int32), ("vn", C.c_int32),
+        ("sigmoid_weights", C.c_int32), ("filter_estimates", C.c_int32), ("second_largest", C.c_int32),
+        ("min_component", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "casa_version": (C.c_int, []),
+    "casa_last_error": (C.c_char_p, []),
+    "casa_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "casa_destroy": (C.c_int, [C.c_void_p]),
+    "casa_ransac_workspace_bytes": (C.c_size_t, [C.POINTER(RansacParams)]),
+    "casa_ransac_vote": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.POINTER(RansacDebug), C.c_void_p]),
+    "casa_ransac_vote_host": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "casa_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "casa_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "casa_selftest_filter": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_float,
+                                       C.POINTER(C.c_uint64)]),
+    "casa_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_handles = {}
+
+
+def build(verbose=False):
+    """Compile csrc/casa_api.cu for sm_100a into csrc/libcasapose_b200.so (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(CSRC, "casa_api.cu")
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise CasaError("nvcc failed:\n" + res.stdout + res.stderr)
+    return res.stderr if verbose else LIB_PATH
+
+
+def _sources_newer_than_lib():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    inc = os.path.join(_HERE, "..", "include", "casapose_b200.h")
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [inc]
+    return any(os.path.exists(f) and os.path.getmtime(f) > t for f in files)
+
+
+def lib():
+    """Load the shared library, declaring every export of include/casapose_b200.h."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise CasaError(
+                    "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+            L = C.CDLL(LIB_PATH)
+            for name, (res, args) in EXPORTS.items():
+                fn = getattr(L, name)  # AttributeError here = header and library disagree
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CasaError("casapose_b200 error %d: %s" % (rc, lib().casa_last_error().decode()))
+
+
+def handle(device):
+    """One library handle per (device, thread)."""
+    key = (int(device), threading.get_ident())
+    h = _handles.get(key)
+    if h is None:
+        hp = C.c_void_p()
+        check(lib().casa_create(int(device), C.byref(hp)))
+        h = hp
+        _handles[key] = h
+    return h
+
+
+def status_names(word):
+    return [n for bit, n in STATUS_BITS.items() if word & bit]

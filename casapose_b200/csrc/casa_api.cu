@@ -1,0 +1,371 @@
+// C ABI of casapose_b200 (include/casapose_b200.h): host-side orchestration of the kernels.
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "compaction.cuh"
+#include "ls_vote.cuh"
+#include "predicate.cuh"
+#include "ransac.cuh"
+#include "selftest.cuh"
+
+using namespace casa;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(CASA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct casa_handle {
+  int device = 0;
+  int sm_count = 148;
+  void* ws_mem = nullptr;
+  size_t ws_bytes = 0;
+  void* io_mem = nullptr;  // device staging of the host-buffer entry points
+  size_t io_bytes = 0;
+  int* pinned = nullptr;   // CTRL_WORDS ints, page-locked
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint32_t last_status = 0;
+  int64_t last_launches = 0;
+  int score_p = 8;  // hypotheses per lane in k_score
+};
+
+extern "C" int casa_version(void) { return CASA_VERSION; }
+extern "C" const char* casa_last_error(void) { return g_err; }
+
+extern "C" int casa_create(int device, casa_handle** out) {
+  if (!out) return fail(CASA_ERR_INVALID, "casa_create: out is NULL");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(CASA_ERR_NODEVICE, "casa_create: no CUDA device");
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= n) return fail(CASA_ERR_INVALID, "casa_create: device %d out of range (%d devices)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(CASA_ERR_NODEVICE, "casa_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  casa_handle* h = new casa_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaHostAlloc((void**)&h->pinned, CTRL_WORDS * sizeof(int), cudaHostAllocDefault));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+  const char* sp = getenv("CASA_SCORE_P");
+  if (sp && atoi(sp) == 4) h->score_p = 4;
+  *out = h;
+  return CASA_OK;
+}
+
+extern "C" int casa_destroy(casa_handle* h) {
+  if (!h) return CASA_OK;
+  cudaSetDevice(h->device);
+  if (h->ws_mem) cudaFree(h->ws_mem);
+  if (h->io_mem) cudaFree(h->io_mem);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return CASA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+
+namespace {
+
+struct Layout {
+  Dims d;
+  size_t off_bits, off_tile_cnt, off_tile_base, off_pix, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
+      off_job_rounds, off_job_selthr, off_win_ratio, off_win_pts, off_hyp_true, off_hyp_filt, off_exact_list,
+      off_n_exact, off_counts, off_items, off_ctrl, off_sums, off_stats, total;
+};
+
+size_t bump(size_t& cur, size_t bytes) {
+  const size_t o = cur;
+  cur += (bytes + 255) & ~size_t(255);
+  return o;
+}
+
+
+int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
+  if (!p) return fail(CASA_ERR_INVALID, "params is NULL");
+  if (p->b < 1 || p->h < 1 || p->w < 1 || p->h > 65535 || p->w > 65535)
+    return fail(CASA_ERR_INVALID, "bad shape b=%d h=%d w=%d", p->b, p->h, p->w);
+  if (p->oc < 1 || p->oc > 32) return fail(CASA_ERR_INVALID, "oc=%d outside 1..32", p->oc);
+  if (p->vn < 1 || p->vn > 16) return fail(CASA_ERR_INVALID, "vn=%d outside 1..16", p->vn);
+  if (p->round_hyp_num < 1 || p->round_hyp_num > 4096) return fail(CASA_ERR_INVALID, "round_hyp_num=%d outside 1..4096", p->round_hyp_num);
+  if (p->max_iter < 1 || p->max_iter > 64) return fail(CASA_ERR_INVALID, "max_iter=%d outside 1..64", p->max_iter);
+  if ((long long)p->b * p->oc > 65535) return fail(CASA_ERR_INVALID, "b*oc=%lld exceeds 65535 jobs per call", (long long)p->b * p->oc);
+  if ((long long)p->h * p->w > (1ll << 30)) return fail(CASA_ERR_INVALID, "image too large");
+  if ((long long)p->round_hyp_num * p->max_iter >= (1 << 24)) return fail(CASA_ERR_INVALID, "hn*max_iter must stay below 2^24");
+  Dims& d = L.d;
+  d.b = p->b; d.h = p->h; d.w = p->w; d.oc = p->oc; d.vn = p->vn; d.hn = p->round_hyp_num; d.max_iter = p->max_iter;
+  d.hw = p->h * p->w;
+  d.J = p->b * p->oc;
+  d.nct = (d.hw + kCountTile - 1) / kCountTile;
+  d.cap = p->pix_capacity > 0 ? p->pix_capacity : d.hw;
+  const int tile = kScoreTile;
+  (void)score_p;
+  const long long items = (long long)d.b * ((long long)d.cap / tile + d.oc + 1) * d.vn;
+  if (items > (1ll << 30)) return fail(CASA_ERR_INVALID, "too many work items");
+  d.max_items = (int)items;
+  d.image_offset = p->image_offset;
+  d.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFull);
+  d.seed_hi = (uint32_t)(p->seed >> 32);
+  d.min_num = p->min_num; d.max_num = p->max_num; d.confidence = p->confidence;
+  d.force_exact = p->force_exact;
+  size_t cur = 0;
+  const size_t J = d.J, jv = J * d.vn, jvh = jv * d.hn;
+  L.off_bits = bump(cur, (size_t)d.b * d.hw * 4);
+  L.off_tile_cnt = bump(cur, J * d.nct * 4);
+  L.off_tile_base = bump(cur, J * d.nct * 4);
+  L.off_pix = bump(cur, (size_t)d.b * d.cap * 4);
+  L.off_job_tn0 = bump(cur, J * 4);
+  L.off_job_tn = bump(cur, J * 4);
+  L.off_job_off = bump(cur, J * 4);
+  L.off_job_flags = bump(cur, J * 4);
+  L.off_job_rounds = bump(cur, J * 4);
+  L.off_job_selthr = bump(cur, J * 4);
+  L.off_win_ratio = bump(cur, jv * 4);
+  L.off_win_pts = bump(cur, jv * 8);
+  L.off_hyp_true = bump(cur, jvh * 8);
+  L.off_hyp_filt = bump(cur, jvh * 8);
+  L.off_exact_list = bump(cur, jvh * 4);
+  L.off_n_exact = bump(cur, jv * 4);
+  L.off_counts = bump(cur, jvh * 4);
+  L.off_items = bump(cur, (size_t)d.max_items * 8);
+  L.off_ctrl = bump(cur, CTRL_WORDS * 4);
+  L.off_sums = bump(cur, jv * 5 * 8);
+  L.off_stats = bump(cur, 4 * 8);
+  L.total = cur;
+  return CASA_OK;
+}
+
+WS make_ws(const Layout& L, void* base, bool stats) {
+  char* b = (char*)base;
+  WS w;
+  w.bits = (uint32_t*)(b + L.off_bits);
+  w.tile_cnt = (int*)(b + L.off_tile_cnt);
+  w.tile_base = (int*)(b + L.off_tile_base);
+  w.pix = (uint32_t*)(b + L.off_pix);
+  w.job_tn0 = (int*)(b + L.off_job_tn0);
+  w.job_tn = (int*)(b + L.off_job_tn);
+  w.job_off = (int*)(b + L.off_job_off);
+  w.job_flags = (int*)(b + L.off_job_flags);
+  w.job_rounds = (int*)(b + L.off_job_rounds);
+  w.job_selthr = (float*)(b + L.off_job_selthr);
+  w.win_ratio = (float*)(b + L.off_win_ratio);
+  w.win_pts = (float2*)(b + L.off_win_pts);
+  w.hyp_true = (float2*)(b + L.off_hyp_true);
+  w.hyp_filt = (float2*)(b + L.off_hyp_filt);
+  w.exact_list = (int*)(b + L.off_exact_list);
+  w.n_exact = (int*)(b + L.off_n_exact);
+  w.counts = (int*)(b + L.off_counts);
+  w.items = (int2*)(b + L.off_items);
+  w.ctrl = (int*)(b + L.off_ctrl);
+  w.sums = (double*)(b + L.off_sums);
+  w.stats = stats ? (unsigned long long*)(b + L.off_stats) : nullptr;
+  return w;
+}
+
+int ensure(void** mem, size_t* have, size_t need) {
+  if (*have >= need) return CASA_OK;
+  if (*mem) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(*mem));
+    *mem = nullptr;
+    *have = 0;
+  }
+  CUDA_TRY(cudaMalloc(mem, need));
+  *have = need;
+  return CASA_OK;
+}
+
+template <int H>
+int launch_score(casa_handle* h, const ScoreArgs& a, cudaStream_t st) {
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score<H>, kScoreThreads, 0));
+  if (occ < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
+  k_score<H><<<h->sm_count * occ, kScoreThreads, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return CASA_OK;
+}
+
+}  // namespace
+
+extern "C" size_t casa_ransac_workspace_bytes(const casa_ransac_params* p) {
+  Layout L;
+  if (make_layout(p, 4, L) != CASA_OK) return 0;
+  return L.total;
+}
+
+// ------------------------------------------------------------------------------------------------ ransac vote
+
+extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, const float* mask, const float* vertex,
+                                const int32_t* idxs, const float* selection, float* out_points,
+                                const casa_ransac_debug* debug, void* stream) {
+  if (!h) return fail(CASA_ERR_INVALID, "handle is NULL");
+  if (!mask || !vertex || !out_points) return fail(CASA_ERR_INVALID, "mask / vertex / out_points must not be NULL");
+  Layout L;
+  int rc = make_layout(p, h->score_p, L);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rc = ensure(&h->ws_mem, &h->ws_bytes, L.total);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  casa_ransac_debug dbg;
+  memset(&dbg, 0, sizeof(dbg));
+  if (debug) dbg = *debug;
+  const Dims& d = L.d;
+  WS ws = make_ws(L, h->ws_mem, dbg.stats != nullptr);
+  const FilterConsts fc = filter_consts(p->inlier_thresh, p->force_exact);
+  int64_t launches = 0;
+
+  CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
+  if (ws.stats) CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
+
+  const int vec4 = ((d.oc & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
+  k_mask_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d, vec4);
+  k_scan_jobs<<<d.b, 256, 0, st>>>(ws, d);
+  k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
+  launches += 3;
+  if ((float)d.hw > p->max_num) {
+    k_cap_filter<<<d.J, 1024, 0, st>>>(ws, d, selection);
+    ++launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+
+  ScoreArgs sa;
+  sa.ws = ws;
+  sa.d = d;
+  sa.fc = fc;
+  sa.vertex = vertex;
+  for (int rnd = 0; rnd < d.max_iter; ++rnd) {
+    k_hypgen<<<d.J, 256, 0, st>>>(ws, d, fc, vertex, idxs, rnd, dbg.hyps);
+    k_plan<<<1, 1024, 0, st>>>(ws, d, kScoreTile);
+    CUDA_TRY(cudaGetLastError());
+    rc = h->score_p == 4 ? launch_score<4>(h, sa, st) : launch_score<8>(h, sa, st);
+    if (rc) return rc;
+    k_update<<<d.J, 256, 0, st>>>(ws, d, rnd, dbg);
+    launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    // the reference's data-dependent `while` (:318): one 32-byte read-back per round
+    CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h->pinned[CTRL_NACTIVE] == 0) break;
+  }
+  k_refine<<<dim3(d.vn, d.J), 256, 0, st>>>(ws, d, fc, vertex);
+  k_solve<<<(d.J + 127) / 128, 128, 0, st>>>(ws, d, out_points, dbg);
+  launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  if (dbg.pix) CUDA_TRY(cudaMemcpyAsync(dbg.pix, ws.pix, (size_t)d.b * d.cap * 4, cudaMemcpyDeviceToDevice, st));
+  if (dbg.stats) CUDA_TRY(cudaMemcpyAsync(dbg.stats, ws.stats, 4 * 8, cudaMemcpyDeviceToDevice, st));
+  h->last_status = (uint32_t)h->pinned[CTRL_STATUS];
+  h->last_launches = launches;
+  if (h->last_status & CASA_STATUS_PIX_OVERFLOW)
+    return fail(CASA_ERR_WORKSPACE, "pixel lists exceed pix_capacity=%d (mask is not one-hot?); retry with a larger pix_capacity", d.cap);
+  if (h->last_status & CASA_STATUS_IDX_RANGE) return fail(CASA_ERR_INPUT, "caller-supplied idxs outside [0, tn)");
+  return CASA_OK;
+}
+
+extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
+                                     const float* vertex_host, float* out_points_host) {
+  if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
+  if (!mask_host || !vertex_host || !out_points_host) return fail(CASA_ERR_INVALID, "host buffers must not be NULL");
+  Layout L;
+  int rc = make_layout(p, h->score_p, L);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t hw = (size_t)p->h * p->w;
+  const size_t mask_b = ((size_t)p->b * hw * p->oc * 4 + 255) & ~size_t(255);
+  const size_t vert_b = ((size_t)p->b * hw * p->vn * 2 * 4 + 255) & ~size_t(255);
+  const size_t out_b = (size_t)p->b * p->oc * p->vn * 2 * 4;
+  rc = ensure(&h->io_mem, &h->io_bytes, mask_b + vert_b + out_b);
+  if (rc) return rc;
+  float* dmask = (float*)h->io_mem;
+  float* dvert = (float*)((char*)h->io_mem + mask_b);
+  float* dout = (float*)((char*)h->io_mem + mask_b + vert_b);
+  cudaStream_t st = h->own_stream;
+  CUDA_TRY(cudaMemcpyAsync(dmask, mask_host, (size_t)p->b * hw * p->oc * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dvert, vertex_host, (size_t)p->b * hw * p->vn * 2 * 4, cudaMemcpyHostToDevice, st));
+  rc = casa_ransac_vote(h, p, dmask, dvert, nullptr, nullptr, dout, nullptr, (void*)st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return CASA_OK;
+}
+
+extern "C" int casa_last_status(casa_handle* h, uint32_t* status) {
+  if (!h || !status) return fail(CASA_ERR_INVALID, "NULL argument");
+  *status = h->last_status;
+  return CASA_OK;
+}
+
+extern "C" int casa_last_launches(casa_handle* h, int64_t* launches) {
+  if (!h || !launches) return fail(CASA_ERR_INVALID, "NULL argument");
+  *launches = h->last_launches;
+  return CASA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ self tests
+
+extern "C" int casa_selftest_filter(casa_handle* h, uint64_t n, uint64_t seed, float inlier_thresh, float spread,
+                                    uint64_t* out4_host) {
+  if (!h || !out4_host) return fail(CASA_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const FilterConsts fc = filter_consts(inlier_thresh, 0);
+  if (!fc.fast_ok) return fail(CASA_ERR_INVALID, "inlier_thresh=%g is outside the filtered range", inlier_thresh);
+  unsigned long long* dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dout, 4 * 8));
+  CUDA_TRY(cudaMemset(dout, 0, 4 * 8));
+  k_selftest_filter<<<h->sm_count * 8, 256>>>(n, (uint32_t)seed, (uint32_t)(seed >> 32), fc, acos((double)inlier_thresh), spread, dout);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out4_host, dout, 4 * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaFree(dout));
+  return CASA_OK;
+}
+
+extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflops, double* ms_out) {
+  if (!h || !tflops) return fail(CASA_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  float* dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dout, 4));
+  const int iters = 8192, blocks = h->sm_count * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(h->ev0, 0));
+    switch (variant) {
+      case 0: k_fma_peak<0><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 1: k_fma_peak<1><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 2: k_fma_peak<2><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      default: k_fma_peak<3><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, 0));
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  CUDA_TRY(cudaFree(dout));
+  // variants 0-2: 16 FMA = 32 FLOP per thread-iteration; variant 3: 16 units x 11 algorithmic FLOP
+  const double flop_per_iter = variant <= 2 ? 32.0 : 16.0 * 11.0;
+  *tflops = (double)blocks * 256.0 * iters * flop_per_iter / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return CASA_OK;
+}

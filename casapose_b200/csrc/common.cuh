@@ -1,0 +1,80 @@
+// Shared definitions of the casapose_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/casapose_b200.h"
+
+namespace casa {
+
+constexpr int kCountTile = 1024;   // pixels per block in the mask / scatter kernels (256 thr x 4)
+constexpr int kScoreWarps = 8;     // warps per scoring block
+constexpr int kScoreThreads = kScoreWarps * 32;
+
+// job flag bits
+constexpr int JOB_GATED = 1;     // foreground_num < min_num  -> zeros   (ransac_voting.py:290)
+constexpr int JOB_NEEDS_CAP = 2; // foreground_num > max_num             (ransac_voting.py:295)
+constexpr int JOB_ACTIVE = 4;    // RANSAC loop still running             (ransac_voting.py:318)
+constexpr int JOB_OVERFLOW = 8;  // pixel list did not fit
+
+// ctrl words
+constexpr int CTRL_NITEMS = 0;
+constexpr int CTRL_WORK = 1;
+constexpr int CTRL_NACTIVE = 2;
+constexpr int CTRL_STATUS = 3;
+constexpr int CTRL_WORDS = 8;
+
+// hypothesis classes written by k_hypgen
+//   normal : hyp_filt == hyp_true, scored by the filtered predicate
+//   zero   : count is 0 by construction (invalid-sum guard :241-243 or non-finite) -> hyp_filt = NaN
+//   exact  : scored only by the exact predicate (exact list)                        -> hyp_filt = NaN
+
+// Constants of the filtered predicate, derived on the host in double (filter_consts()).
+struct FilterConsts {
+  float thr;     // inlier_thresh as float32
+  float k_lo;    // tan(theta0 - delta), rounded down
+  float rho;     // k_hi / k_lo, rounded up (> 1)
+  float kappa;   // 1 - 1/rho, rounded up:  |p| < rho a  <=>  |p| - a - kappa |p| < 0
+  int fast_ok;   // 0 -> thresholds outside the proven range, score everything exactly
+};
+
+struct WS {
+  uint32_t* bits;      // [b*h*w]        class-membership bit mask per pixel
+  int* tile_cnt;       // [b][oc][nct]   per count-tile class counts
+  int* tile_base;      // [b][oc][nct]   exclusive prefix of tile_cnt
+  uint32_t* pix;       // [b][cap]       compacted pixel lists, (y<<16|x), raster order per class
+  int* job_tn0;        // [J]
+  int* job_tn;         // [J]
+  int* job_off;        // [J]
+  int* job_flags;      // [J]
+  int* job_rounds;     // [J]
+  float* job_selthr;   // [J]            max_num / foreground_num          (:298)
+  float* win_ratio;    // [J][vn]
+  float2* win_pts;     // [J][vn]
+  float2* hyp_true;    // [J][vn][hn]
+  float2* hyp_filt;    // [J][vn][hn]
+  int* exact_list;     // [J][vn][hn]
+  int* n_exact;        // [J][vn]
+  int* counts;         // [J][vn][hn]
+  int2* items;         // [max_items]    scoring work items {job, v<<20 | tile}
+  int* ctrl;           // [CTRL_WORDS]
+  double* sums;        // [J][vn][5]     sum nx*nx, nx*ny, ny*ny, nx*b, ny*b
+  unsigned long long* stats;  // [4]
+};
+
+struct Dims {
+  int b, h, w, oc, vn, hn, max_iter;
+  int hw, J, nct, cap, max_items;
+  int image_offset;
+  uint32_t seed_lo, seed_hi;
+  float min_num, max_num, confidence;
+  int force_exact;
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+}  // namespace casa

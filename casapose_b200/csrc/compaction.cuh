@@ -1,0 +1,218 @@
+// K1 — ordered per-class mask compaction.
+//
+// Replaces  coords = reverse(where(mask != 0)) + 0.5 ; direct = boolean_mask(vertex, mask)
+// (/root/reference/casapose/pose_estimation/ransac_voting.py:287-308) for all (image, class)
+// pairs of the batch at once:
+//   k_mask_bits   reads the float mask ONCE (the only pass over [b,h,w,oc]), writes one
+//                 class-membership word per pixel and per-tile class counts (warp ballots);
+//   k_scan_jobs   exclusive prefix over the tiles of each (image, class), job table
+//                 (foreground_num gate :290, down-sampling threshold :298);
+//   k_scatter     raster-order scatter of packed pixel coordinates (y<<16 | x) — the order is
+//                 semantically required because hypothesis indices address this list (:216);
+//   k_cap_filter  in-place ordered filter  selection < max_num / foreground_num  (:295-301).
+// The vector field is NOT copied: the scoring kernels gather (dy,dx) straight from `vertex`
+// through the pixel list, so only masked pixels of the 18-channel field are ever read.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace casa {
+
+__global__ void __launch_bounds__(256) k_mask_bits(const float* __restrict__ mask, WS ws, Dims d, int vec4) {
+  const int img = blockIdx.y, tile = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int scnt[32];
+  if (tid < 32) scnt[tid] = 0;
+  __syncthreads();
+  const float* mimg = mask + (size_t)img * d.hw * d.oc;
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = tile * kCountTile + k * 256 + tid;
+    uint32_t m = 0;
+    if (p < d.hw) {
+      const float* row = mimg + (size_t)p * d.oc;
+      if (vec4) {
+        for (int c4 = 0; c4 < d.oc; c4 += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + c4));
+          m |= (uint32_t)(v.x != 0.f) << c4;
+          m |= (uint32_t)(v.y != 0.f) << (c4 + 1);
+          m |= (uint32_t)(v.z != 0.f) << (c4 + 2);
+          m |= (uint32_t)(v.w != 0.f) << (c4 + 3);
+          bad |= (v.x != 0.f && v.x != 1.f) || (v.y != 0.f && v.y != 1.f) || (v.z != 0.f && v.z != 1.f) ||
+                 (v.w != 0.f && v.w != 1.f);
+        }
+      } else {
+        for (int c = 0; c < d.oc; ++c) {
+          const float v = __ldg(row + c);
+          m |= (uint32_t)(v != 0.f) << c;
+          bad |= (v != 0.f && v != 1.f);
+        }
+      }
+      ws.bits[(size_t)img * d.hw + p] = m;
+    }
+    for (int c = 0; c < d.oc; ++c) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
+      if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+    }
+  }
+  if (bad) atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_MASK_NOT_BINARY);
+  __syncthreads();
+  if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
+}
+
+// one block per image
+__global__ void __launch_bounds__(256) k_scan_jobs(WS ws, Dims d) {
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int swarp[8];
+  __shared__ int srun;
+  __shared__ int stn0[32];
+  for (int c = 0; c < d.oc; ++c) {
+    const int* cnt = ws.tile_cnt + ((size_t)img * d.oc + c) * d.nct;
+    int* base = ws.tile_base + ((size_t)img * d.oc + c) * d.nct;
+    if (tid == 0) srun = 0;
+    __syncthreads();
+    for (int s = 0; s < d.nct; s += 256) {
+      const int i = s + tid;
+      const int v = i < d.nct ? cnt[i] : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) swarp[warp] = x;
+      __syncthreads();
+      int woff = 0;
+      for (int k = 0; k < warp; ++k) woff += swarp[k];
+      const int run = srun;
+      if (i < d.nct) base[i] = run + woff + x - v;
+      __syncthreads();
+      if (tid == 255) srun = run + woff + x;
+      __syncthreads();
+    }
+    if (tid == 0) stn0[c] = srun;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int off = 0;
+    for (int c = 0; c < d.oc; ++c) {
+      const int job = img * d.oc + c;
+      const int tn0 = stn0[c];
+      int flags = 0;
+      const float fg = (float)tn0;  // tf.reduce_sum of a {0,1} mask (:287)
+      if (fg < d.min_num) flags |= JOB_GATED;               // :290
+      float thr = 1.f;
+      if (fg > d.max_num) {                                 // :295
+        flags |= JOB_NEEDS_CAP;
+        thr = __fdiv_rn(d.max_num, fg);                     // :298
+      }
+      if (off + tn0 > d.cap) {
+        flags |= JOB_GATED | JOB_OVERFLOW;
+        atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_PIX_OVERFLOW);
+      }
+      ws.job_tn0[job] = tn0;
+      ws.job_tn[job] = (flags & JOB_OVERFLOW) ? 0 : tn0;
+      ws.job_off[job] = off;
+      ws.job_flags[job] = flags;
+      ws.job_rounds[job] = 0;
+      ws.job_selthr[job] = thr;
+      if (!(flags & JOB_OVERFLOW)) off += tn0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(WS ws, Dims d) {
+  const int img = blockIdx.y, tile = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int wcnt[32][32];  // [class][slot*8 + warp]
+  uint32_t m[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = tile * kCountTile + k * 256 + tid;
+    m[k] = p < d.hw ? ws.bits[(size_t)img * d.hw + p] : 0u;
+  }
+  for (int c = 0; c < d.oc; ++c) {
+    if (ws.tile_cnt[((size_t)img * d.oc + c) * d.nct + tile] == 0) continue;  // block-uniform
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (m[k] >> c) & 1u);
+      if (lane == 0) wcnt[c][k * 8 + warp] = __popc(bal);
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < d.oc; c += 8) {
+    if (ws.tile_cnt[((size_t)img * d.oc + c) * d.nct + tile] == 0) continue;
+    const int v = wcnt[c][lane];
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    wcnt[c][lane] = x - v;  // exclusive
+  }
+  __syncthreads();
+  for (int c = 0; c < d.oc; ++c) {
+    if (ws.tile_cnt[((size_t)img * d.oc + c) * d.nct + tile] == 0) continue;
+    const int job = img * d.oc + c;
+    if (ws.job_flags[job] & JOB_OVERFLOW) continue;
+    const int tbase = ws.tile_base[((size_t)img * d.oc + c) * d.nct + tile];
+    uint32_t* out = ws.pix + (size_t)img * d.cap + ws.job_off[job];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool bit = (m[k] >> c) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      if (bit) {
+        const int p = tile * kCountTile + k * 256 + tid;
+        const int y = p / d.w, x = p - y * d.w;
+        out[tbase + wcnt[c][k * 8 + warp] + __popc(bal & lanemask_lt())] = ((uint32_t)y << 16) | (uint32_t)x;
+      }
+    }
+  }
+}
+
+// one block of 1024 threads per job; only jobs with JOB_NEEDS_CAP do anything
+__global__ void __launch_bounds__(1024) k_cap_filter(WS ws, Dims d, const float* __restrict__ selection) {
+  const int job = blockIdx.x;
+  const int flags = ws.job_flags[job];
+  if (!(flags & JOB_NEEDS_CAP) || (flags & JOB_GATED)) return;
+  const int img = job / d.oc, cls = job - img * d.oc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tn0 = ws.job_tn0[job];
+  const float thr = ws.job_selthr[job];
+  uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
+  __shared__ int swarp[32];
+  __shared__ int srun;
+  if (tid == 0) srun = 0;
+  __syncthreads();
+  for (int s = 0; s < tn0; s += 1024) {
+    const int i = s + tid;
+    bool keep = false;
+    uint32_t pk = 0;
+    if (i < tn0) {
+      pk = pix[i];
+      const int x = pk & 0xFFFFu, y = pk >> 16;
+      const float sel = selection ? selection[((size_t)job * d.h + y) * d.w + x]
+                                  : philox_selection((uint32_t)(y * d.w + x), (uint32_t)cls,
+                                                     (uint32_t)(d.image_offset + img), d.seed_lo, d.seed_hi);
+      keep = sel < thr;  // :297-299
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) swarp[warp] = __popc(bal);
+    __syncthreads();  // all reads of this chunk are done
+    int woff = 0;
+    for (int k = 0; k < warp; ++k) woff += swarp[k];
+    const int run = srun;
+    if (keep) pix[run + woff + __popc(bal & lanemask_lt())] = pk;
+    __syncthreads();
+    if (tid == 1023) srun = run + woff + __popc(bal);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ws.job_tn[job] = srun;
+    if (srun == 0) atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_EMPTY_AFTER_CAP);
+  }
+}
+
+}  // namespace casa

@@ -1,0 +1,159 @@
+// The inlier predicate of voting_for_hypothesis
+// (/root/reference/casapose/pose_estimation/ransac_voting.py:230-249) in two forms:
+//
+//  * exact_inlier(): the reference's float32 op sequence, one IEEE rounding per TensorFlow
+//    op (__f*_rn intrinsics are never contracted into FMAs).  This DEFINES the result.
+//
+//  * the filtered predicate: per (pixel, keypoint) the unit direction d^ = d/|d| is turned
+//    into two linear forms of hd = fl(h - c) (the same rounded difference the reference
+//    uses, :236):
+//        p  = d^ x hd            (= |hd| sin(theta))
+//        a  = k_lo * (d^ . hd)   (= k_lo |hd| cos(theta)),     a_hi = rho * a
+//    "|p| < a"    proves  theta < theta0 - delta  => the reference says inlier,
+//    "|p| >= a_hi" proves theta > theta0 + delta  => the reference says outlier,
+//    where theta0 = acos(inlier_thresh) and delta covers (i) the worst-case rounding of
+//    the reference's own sequence around the true cosine and (ii) the rounding of the
+//    filter (derivation in DESIGN.md section "Filtered predicate").  Units in between
+//    (~1e-5 of all units) are re-evaluated with exact_inlier().  Vote counts are
+//    therefore bit-identical to the exact sequence while the common path costs
+//    7 FP32-pipe + 2 compare instructions per unit instead of ~30.
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace casa {
+
+constexpr float kEps1e6 = 1e-6f;          // python 1e-6 converted to float32 (:226, :240, :242)
+constexpr float kDirMax = 1073741824.0f;  // 2^30: direction components above this take the exact path
+constexpr float kHypMax = 1.152921504606846976e18f;  // 2^60: hypotheses beyond this take the exact path
+constexpr float kNearCentre = 8e-6f;      // hypotheses this close to a pixel centre take the exact path
+
+// ---------------------------------------------------------------- exact (reference) sequence
+
+// tf.norm(direct, axis=-1)  (:238)
+__device__ __forceinline__ float exact_norm(float x, float y) {
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+}
+
+// voting_for_hypothesis for one unit (:236-247). (dx,dy) = direct, nd = exact_norm(dx,dy).
+__device__ __forceinline__ bool exact_inlier(float hx, float hy, float cx, float cy, float dx, float dy,
+                                             float nd, float thr) {
+  const float hdx = __fsub_rn(hx, cx);
+  const float hdy = __fsub_rn(hy, cy);
+  const float nh = exact_norm(hdx, hdy);
+  const bool valid = (nd > kEps1e6) && (nh > kEps1e6) && (fabsf(__fadd_rn(hx, hy)) > kEps1e6);
+  const float dot = __fadd_rn(__fmul_rn(dx, hdx), __fmul_rn(dy, hdy));
+  const float ang = __fdiv_rn(dot, __fmul_rn(nd, nh));
+  return valid && (ang > thr);
+}
+
+// generate_hypothesis for one (h, v) (:219-226).  c0/c1 = coords of the pair, d0/d1 = (dx,dy).
+__device__ __forceinline__ float2 exact_hypothesis(float2 c0, float2 c1, float2 d0, float2 d1) {
+  const float det = __fsub_rn(__fmul_rn(d1.x, d0.y), __fmul_rn(d1.y, d0.x));
+  const float num = __fsub_rn(__fmul_rn(__fsub_rn(c1.y, c0.y), d1.x), __fmul_rn(__fsub_rn(c1.x, c0.x), d1.y));
+  const float u = __fdiv_rn(num, det);
+  float2 hp;
+  hp.x = __fadd_rn(c0.x, __fmul_rn(d0.x, u));
+  hp.y = __fadd_rn(c0.y, __fmul_rn(d0.y, u));
+  if (!(fabsf(det) > kEps1e6)) hp = make_float2(0.f, 0.f);
+  return hp;
+}
+
+// ---------------------------------------------------------------- filtered predicate
+
+struct PixCoef {
+  float cx, cy;  // pixel centre (x+.5, y+.5)
+  float D, E;    // d^ = (dx, dy) / |d|
+  float G, H;    // k_lo * d^
+};
+
+// Returns false if this (pixel, keypoint) cannot use the filter (non-finite or huge direction).
+__device__ __forceinline__ bool make_coef(float cx, float cy, float dx, float dy, float k_lo, PixCoef& c) {
+  c.cx = cx;
+  c.cy = cy;
+  c.D = c.E = c.G = c.H = 0.f;  // zero forms: |0| < 0 is false for lo and hi -> never an inlier
+  const float ax = fabsf(dx), ay = fabsf(dy);
+  if (!(ax <= kDirMax && ay <= kDirMax)) return false;  // also catches NaN / inf
+  const float nd = exact_norm(dx, dy);
+  if (nd > kEps1e6) {  // :240, decided on the exact norm
+    const float inv = 1.0f / nd;
+    c.D = dx * inv;
+    c.E = dy * inv;
+    c.G = k_lo * c.D;
+    c.H = k_lo * c.E;
+  }
+  return true;
+}
+
+// One unit of the filter.  inlier-for-sure <=> sign(tlo), maybe-inlier <=> sign(thi).
+// Negated form on purpose: NaN (canonical, sign 0) and +0 are "not inlier", and neither chain can yield -0.
+__device__ __forceinline__ void filter_unit(float cx, float cy, float D, float nE, float nG, float nH, float nkappa,
+                                            float hx, float hy, float& tlo, float& thi) {
+  const float hdx = hx - cx;  // same rounded difference as the reference (:236)
+  const float hdy = hy - cy;
+  const float pv = fmaf(D, hdy, __fmul_rn(nE, hdx));
+  tlo = fmaf(nG, hdx, fmaf(nH, hdy, fabsf(pv)));
+  thi = fmaf(nkappa, fabsf(pv), tlo);
+}
+
+__device__ __forceinline__ void filter_test(const PixCoef& c, float hx, float hy, float kappa, bool& lo, bool& hi) {
+  float tlo, thi;
+  filter_unit(c.cx, c.cy, c.D, -c.E, -c.G, -c.H, -kappa, hx, hy, tlo, thi);
+  lo = (__float_as_uint(tlo) >> 31) != 0u;
+  hi = (__float_as_uint(thi) >> 31) != 0u;
+}
+
+// 0 = normal (filter), 1 = zero count by construction, 2 = exact list
+__device__ __forceinline__ int classify_hypothesis(float hx, float hy, bool fast_ok) {
+  if (!(fabsf(hx) <= 3.0e38f && fabsf(hy) <= 3.0e38f)) return 1;  // inf / NaN: every ang is NaN or 0/inf
+  if (!(fabsf(__fadd_rn(hx, hy)) > kEps1e6)) return 1;             // :241-243 guard fails for every pixel
+  if (!fast_ok) return 2;
+  if (fabsf(hx) > kHypMax || fabsf(hy) > kHypMax) return 2;        // hd^2 may overflow in the reference
+  bool nearx = false, neary = false;
+  if (fabsf(hx) < 4194304.f) nearx = fabsf(hx - (floorf(hx) + 0.5f)) <= kNearCentre;
+  if (fabsf(hy) < 4194304.f) neary = fabsf(hy - (floorf(hy) + 0.5f)) <= kNearCentre;
+  if (nearx && neary) return 2;  // |hd| may be <= 1e-6 for one pixel (:240 norm_hyp guard)
+  return 0;
+}
+
+// ---------------------------------------------------------------- host: filter constants
+
+inline FilterConsts filter_consts(float inlier_thresh, int force_exact) {
+  FilterConsts f;
+  f.thr = inlier_thresh;
+  f.k_lo = 0.f;
+  f.rho = 1.f;
+  f.kappa = 0.f;
+  f.fast_ok = 0;
+  const double thr = (double)inlier_thresh;
+  if (force_exact || !(thr >= 0.5 && thr <= 0.9999)) return f;
+  const double u = 5.9604644775390625e-8;  // 2^-24
+  const double theta0 = acos(thr);
+  const double s0 = sin(theta0);
+  // |ang_reference - cos(theta)| <= (u + 8 u thr) (1 + small): dot (u/thr + u), two norms (2u each),
+  // their product (u), the divide (u), relative to cos(theta) ~ thr.
+  const double dC = 1.05 * (u + 8.0 * u * thr);
+  const double d_ref = dC / s0;   // angular half-width from the reference's own rounding
+  const double d_fil = 8.0 * u;   // angular error of the filter's two linear forms (< 3.5 u)
+  const double delta = 1.5 * (d_ref + d_fil);
+  if (!(theta0 - delta > 1e-3)) return f;
+  // verify the band really covers dC on both sides (curvature of cos)
+  if (!(cos(theta0 - delta) >= thr + dC && cos(theta0 + delta) <= thr - dC)) return f;
+  const double k_lo = tan(theta0 - delta);
+  const double k_hi = tan(theta0 + delta);
+  float klo_f = (float)k_lo;
+  klo_f = nextafterf(klo_f, 0.f);  // rounded down
+  klo_f = nextafterf(klo_f, 0.f);
+  float rho_f = (float)(k_hi / (double)klo_f);
+  for (int i = 0; i < 3; ++i) rho_f = nextafterf(rho_f, 2.f);  // rounded up, + the rounding of rho*a
+  f.k_lo = klo_f;
+  f.rho = rho_f;
+  float kap = (float)(1.0 - 1.0 / (double)rho_f);
+  for (int i = 0; i < 2; ++i) kap = nextafterf(kap, 1.f);
+  f.kappa = kap;
+  f.fast_ok = 1;
+  return f;
+}
+
+}  // namespace casa

@@ -1,0 +1,149 @@
+/*
+ * casapose_b200 — C ABI of the B200-native (sm_100a) keypoint-voting hot path.
+ *
+ * The reference (fraunhoferhhi/casapose) has no FFI / plugin / custom-op interface: the
+ * boundary of this path is plain Python taking tf.Tensors.  Every entry point below
+ * therefore cites the reference PYTHON interface it stands behind; the Python package
+ * casapose_b200.pose_estimation keeps those names and signatures and hands raw device
+ * pointers (obtained through DLPack) to this library via ctypes.  INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative casa_status; the message of the
+ *     last failure on the calling thread is casa_last_error().  No exception crosses.
+ *   - all tensors are dense, C-contiguous, float32 NHWC exactly like the reference's
+ *     tensors; the caller owns inputs and outputs, the library never frees them.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - a handle is bound to one device, owns the workspace, and is not thread-safe;
+ *     use one handle per stream / thread.
+ */
+#ifndef CASAPOSE_B200_H_
+#define CASAPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CASA_VERSION 100
+
+typedef enum casa_status {
+  CASA_OK = 0,
+  CASA_ERR_INVALID = -1,    /* bad shape / argument */
+  CASA_ERR_CUDA = -2,       /* a CUDA runtime call failed */
+  CASA_ERR_WORKSPACE = -3,  /* pixel lists do not fit pix_capacity (mask is not one-hot) */
+  CASA_ERR_INPUT = -4,      /* device-side input check failed (idx out of range, ...) */
+  CASA_ERR_NODEVICE = -5
+} casa_status;
+
+/* Bits of the device status word (debug.status / casa_last_status). */
+#define CASA_STATUS_MASK_NOT_BINARY 1u  /* a mask value other than 0 or 1 was seen          */
+#define CASA_STATUS_PIX_OVERFLOW 2u     /* sum_c tn0 > pix_capacity for some image            */
+#define CASA_STATUS_IDX_RANGE 4u        /* a caller-supplied idx was outside [0, tn)          */
+#define CASA_STATUS_EMPTY_AFTER_CAP 8u  /* the max_num down-sampling removed every pixel      */
+
+typedef struct casa_handle casa_handle;
+
+int casa_version(void);
+const char* casa_last_error(void);
+
+/* One handle per device/stream user.  device < 0 selects the current device. */
+int casa_create(int device, casa_handle** out);
+int casa_destroy(casa_handle* h);
+
+/*
+ * Parameters of ransac_voting_layer_all_masks
+ * (/root/reference/casapose/pose_estimation/ransac_voting.py:446-484; same names,
+ * same defaults: inlier_thresh=0.99, confidence=0.99, max_iter=20, min_num=5,
+ * max_num=30000; round_hyp_num is 512 at the reference's call sites,
+ * pose_evaluation.py:50-58).
+ */
+typedef struct casa_ransac_params {
+  int32_t b, h, w;        /* batch, image height, image width                               */
+  int32_t oc;             /* object classes (mask channels), 1..32                          */
+  int32_t vn;             /* keypoints per object (vertex is [b,h,w,vn,2]), 1..16            */
+  int32_t round_hyp_num;  /* hypotheses per round (hn), 1..4096                             */
+  int32_t max_iter;       /* 1..64                                                          */
+  float inlier_thresh;
+  float confidence;
+  float min_num;
+  float max_num;
+  uint64_t seed;          /* Philox4x32-10 key (csrc/philox.cuh); stands in for tf.random   */
+  int32_t image_offset;   /* global index of image 0 (so a sharded batch draws the same     */
+                          /* random numbers as the unsharded one)                           */
+  int32_t pix_capacity;   /* per-image pixel-list capacity; 0 = h*w (enough for one-hot)    */
+  int32_t force_exact;    /* 1 = disable the filtered predicate (tests only)                */
+  int32_t reserved;
+} casa_ransac_params;
+
+/*
+ * Optional per-call debug outputs (device pointers, any may be NULL).  These are the
+ * intermediates of ransac_voting_batch (ransac_voting.py:275-368) the parity tests compare.
+ */
+typedef struct casa_ransac_debug {
+  int32_t* tn0;      /* [b,oc]                 foreground_num                       :287 */
+  int32_t* tn;       /* [b,oc]                 pixels after the max_num cap         :310 */
+  int32_t* rounds;   /* [b,oc]                 cur_iter at loop exit                :341 */
+  int32_t* counts;   /* [b,oc,max_iter,hn,vn]  cur_inlier_counts per round          :327 */
+  int32_t* win_idx;  /* [b,oc,max_iter,vn]     cur_win_idx per round                :328 */
+  float* hyps;       /* [b,oc,max_iter,hn,vn,2] cur_hyp_pts per round               :322 */
+  float* win_pts;    /* [b,oc,vn,2]            all_win_pts at loop exit             :337 */
+  float* win_ratio;  /* [b,oc,vn]              all_win_ratio at loop exit           :338 */
+  float* ata;        /* [b,oc,vn,3]            ATA (xx, xy, yy)                     :361 */
+  float* atb;        /* [b,oc,vn,2]            ATb                                  :362 */
+  int32_t* refined;  /* [b,oc]                 1 if every ATA was invertible        :364 */
+  uint32_t* pix;     /* [b,pix_capacity]       compacted pixel lists (y<<16|x)      :303 */
+  int32_t* pix_off;  /* [b,oc]                 start of each class list inside pix       */
+  uint64_t* stats;   /* [4] filter statistics: units scored, units sent to the exact     */
+                     /*     predicate, exact-list hypotheses, tiles scored exactly        */
+} casa_ransac_debug;
+
+/* Bytes of device workspace the handle will hold for these shapes (grown on demand). */
+size_t casa_ransac_workspace_bytes(const casa_ransac_params* p);
+
+/*
+ * ransac_voting_layer_all_masks(mask, vertex, round_hyp_num, ...) -> [b,oc,vn,2] (x,y) px.
+ *   mask      device float32 [b,h,w,oc]   values in {0,1}
+ *   vertex    device float32 [b,h,w,vn,2] (dy,dx) per keypoint
+ *   idxs      optional device int32 [b,oc,max_iter,hn,vn,2] pixel-pair indices in [0,tn)
+ *             (NULL = draw them from the Philox stream)           ransac_voting.py:319
+ *   selection optional device float32 [b,oc,h,w] in [0,1)          ransac_voting.py:296
+ *   out_points device float32 [b,oc,vn,2]
+ * Asynchronous on `stream` except for one 4-byte read-back per RANSAC round (the
+ * reference's data-dependent `while`, ransac_voting.py:318-347).
+ */
+int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, const float* mask,
+                     const float* vertex, const int32_t* idxs, const float* selection,
+                     float* out_points, const casa_ransac_debug* debug, void* stream);
+
+/*
+ * Same call with HOST buffers: copies mask/vertex host->device (pipelined per image),
+ * runs the path and copies out_points back; returns after the result is on the host.
+ * Host buffers may be pageable or pinned (pinned is faster).
+ */
+int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
+                          const float* vertex_host, float* out_points_host);
+
+/* Device status word of the last casa_ransac_vote on this handle (CASA_STATUS_* bits). */
+int casa_last_status(casa_handle* h, uint32_t* status);
+/* Number of kernels the last call launched on this handle. */
+int casa_last_launches(casa_handle* h, int64_t* launches);
+
+/*
+ * Self-test of the filtered inlier predicate: draws n adversarial (pixel, hypothesis)
+ * pairs concentrated on the decision boundary and compares filter+fallback with the
+ * reference-exact float32 sequence (ransac_voting.py:230-249).
+ * out[0]=tested, out[1]=mismatches, out[2]=sent to exact fallback, out[3]=exact inliers.
+ */
+int casa_selftest_filter(casa_handle* h, uint64_t n, uint64_t seed, float inlier_thresh,
+                         float spread, uint64_t* out4_host);
+
+/* Measured FP32 FMA issue rate of this GPU (TFLOP/s), the denominator for "% of FP32 peak". */
+int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASAPOSE_B200_H_ */

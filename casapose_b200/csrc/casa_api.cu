@@ -43,7 +43,7 @@ struct casa_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t last_status = 0;
   int64_t last_launches = 0;
-  int score_p = 8;  // hypotheses per lane in k_score
+  int score_p = 3;  // min resident blocks/SM the scoring kernel is compiled for (3: 80 regs, 4: 64 regs)
 };
 
 extern "C" int casa_version(void) { return CASA_VERSION; }
@@ -66,7 +66,7 @@ extern "C" int casa_create(int device, casa_handle** out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
-  const char* sp = getenv("CASA_SCORE_P");
+  const char* sp = getenv("CASA_SCORE_MINB");
   if (sp && atoi(sp) == 4) h->score_p = 4;
   *out = h;
   return CASA_OK;
@@ -113,6 +113,7 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   if (p->max_iter < 1 || p->max_iter > 64) return fail(CASA_ERR_INVALID, "max_iter=%d outside 1..64", p->max_iter);
   if ((long long)p->b * p->oc > 65535) return fail(CASA_ERR_INVALID, "b*oc=%lld exceeds 65535 jobs per call", (long long)p->b * p->oc);
   if ((long long)p->h * p->w > (1ll << 30)) return fail(CASA_ERR_INVALID, "image too large");
+  if ((long long)p->h * p->w / kChunk + 1 >= (1 << 24)) return fail(CASA_ERR_INVALID, "image too large for the work-item encoding");
   if ((long long)p->round_hyp_num * p->max_iter >= (1 << 24)) return fail(CASA_ERR_INVALID, "hn*max_iter must stay below 2^24");
   Dims& d = L.d;
   d.b = p->b; d.h = p->h; d.w = p->w; d.oc = p->oc; d.vn = p->vn; d.hn = p->round_hyp_num; d.max_iter = p->max_iter;
@@ -120,7 +121,7 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   d.J = p->b * p->oc;
   d.nct = (d.hw + kCountTile - 1) / kCountTile;
   d.cap = p->pix_capacity > 0 ? p->pix_capacity : d.hw;
-  const int tile = kScoreTile;
+  const int tile = kChunk;
   (void)score_p;
   const long long items = (long long)d.b * ((long long)d.cap / tile + d.oc + 1) * d.vn;
   if (items > (1ll << 30)) return fail(CASA_ERR_INVALID, "too many work items");
@@ -197,12 +198,12 @@ int ensure(void** mem, size_t* have, size_t need) {
   return CASA_OK;
 }
 
-template <int H>
+template <int MINB>
 int launch_score(casa_handle* h, const ScoreArgs& a, cudaStream_t st) {
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score<H>, kScoreThreads, 0));
+  static thread_local int occ = 0;
+  if (occ == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score<MINB>, kScoreThreads, 0));
   if (occ < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
-  k_score<H><<<h->sm_count * occ, kScoreThreads, 0, st>>>(a);
+  k_score<MINB><<<h->sm_count * occ, kScoreThreads, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   return CASA_OK;
 }
@@ -258,9 +259,9 @@ extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, con
   sa.vertex = vertex;
   for (int rnd = 0; rnd < d.max_iter; ++rnd) {
     k_hypgen<<<d.J, 256, 0, st>>>(ws, d, fc, vertex, idxs, rnd, dbg.hyps);
-    k_plan<<<1, 1024, 0, st>>>(ws, d, kScoreTile);
+    k_plan<<<1, 1024, 0, st>>>(ws, d, kChunk);
     CUDA_TRY(cudaGetLastError());
-    rc = h->score_p == 4 ? launch_score<4>(h, sa, st) : launch_score<8>(h, sa, st);
+    rc = h->score_p == 4 ? launch_score<4>(h, sa, st) : launch_score<3>(h, sa, st);
     if (rc) return rc;
     k_update<<<d.J, 256, 0, st>>>(ws, d, rnd, dbg);
     launches += 4;
@@ -346,6 +347,10 @@ extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflop
   CUDA_TRY(cudaSetDevice(h->device));
   float* dout = nullptr;
   CUDA_TRY(cudaMalloc(&dout, 4));
+  // variant + 100*k limits residency to k blocks (8k warps) per SM through dynamic shared memory
+  const int occ_limit = variant / 100;
+  variant %= 100;
+  const size_t dsm = occ_limit > 0 ? (size_t)(220 * 1024 / occ_limit) & ~size_t(1023) : 0;
   const int iters = 8192, blocks = h->sm_count * 8;
   float best = 1e30f;
   for (int rep = 0; rep < 5; ++rep) {
@@ -354,7 +359,20 @@ extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflop
       case 0: k_fma_peak<0><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       case 1: k_fma_peak<1><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       case 2: k_fma_peak<2><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      default: k_fma_peak<3><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 3:
+        if (dsm) CUDA_TRY(cudaFuncSetAttribute(k_fma_peak<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+        k_fma_peak<3><<<blocks, 256, dsm>>>(dout, iters, 1e-9f);
+        break;
+      case 10: k_fma_peak<10><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 11: k_fma_peak<11><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 12: k_fma_peak<12><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 13: k_fma_peak<13><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 14: k_fma_peak<14><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 15: k_fma_peak<15><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 16: k_fma_peak<16><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 17: k_fma_peak<17><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 18: k_fma_peak<18><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      default: return fail(CASA_ERR_INVALID, "unknown fp32 peak variant %d", variant);
     }
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
     CUDA_TRY(cudaEventSynchronize(h->ev1));

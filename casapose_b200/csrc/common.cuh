@@ -35,6 +35,9 @@ struct FilterConsts {
   float k_lo;    // tan(theta0 - delta), rounded down
   float rho;     // k_hi / k_lo, rounded up (> 1)
   float kappa;   // 1 - 1/rho, rounded up:  |p| < rho a  <=>  |p| - a - kappa |p| < 0
+  float c1;      // k_score: a chunk's signs are proven if min|t| >= c1 (|h'| + R)
+  float e1;      // k_score stage 2: evaluation-error bound of t is e1 (|h'| + R)
+  float kappa2;  // k_score stage 2: kappa with the slack for the error of |p|
   int fast_ok;   // 0 -> thresholds outside the proven range, score everything exactly
 };
 

@@ -125,6 +125,9 @@ inline FilterConsts filter_consts(float inlier_thresh, int force_exact) {
   f.k_lo = 0.f;
   f.rho = 1.f;
   f.kappa = 0.f;
+  f.c1 = 0.f;
+  f.e1 = 0.f;
+  f.kappa2 = 0.f;
   f.fast_ok = 0;
   const double thr = (double)inlier_thresh;
   if (force_exact || !(thr >= 0.5 && thr <= 0.9999)) return f;
@@ -152,6 +155,14 @@ inline FilterConsts filter_consts(float inlier_thresh, int force_exact) {
   float kap = (float)(1.0 - 1.0 / (double)rho_f);
   for (int i = 0; i < 2; ++i) kap = nextafterf(kap, 1.f);
   f.kappa = kap;
+  // k_score (chunk-local coordinates, derivation in DESIGN.md "Filtered predicate"):
+  //   * the evaluation error of t is below 6 u (|h'|_1 + |c'|_1) <= 6 sqrt2 u (|h'| + R); doubled -> e1;
+  //   * a unit is uncertain only if -E < T < kappa |p| + E, and then |p| < k_hi |hd| <= k_hi (|h'| + R),
+  //     so min|t| >= (k_hi kappa + e1)(|h'| + R) proves every sign of the chunk.
+  const double e1 = 12.0 * 1.41421357 * u;
+  f.e1 = (float)(1.001 * e1);
+  f.kappa2 = (float)(1.001 * (double)kap);
+  f.c1 = (float)(1.001 * (k_hi * 1.001 * (double)kap + 1.001 * e1));
   f.fast_ok = 1;
   return f;
 }

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int tile_px) {
     int pos = run + woff + x - cnt;
     for (int t = 0; t < nt; ++t)
       for (int v = 0; v < d.vn; ++v) {
-        if (pos < d.max_items) ws.items[pos] = make_int2(job, (v << 20) | t);
+        if (pos < d.max_items) ws.items[pos] = make_int2(job, (v << 24) | t);
         ++pos;
       }
     __syncthreads();
@@ -137,8 +137,8 @@ struct ScoreArgs {
   const float* vertex;
 };
 
-constexpr int kPxPerWarp = 128;                          // pixels of one warp's subset
-constexpr int kScoreTile = kScoreWarps * kPxPerWarp;     // pixels per work item (1024)
+constexpr int kChunk = 128;  // pixels per scoring work item (one warp)
+constexpr int kHypPerLane = 8;
 
 // Exact inlier count of one hypothesis over pixels [t0, t0+npx) of a job, whole warp cooperating.
 __device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const float* __restrict__ vimg, int w, int vn,
@@ -154,126 +154,200 @@ __device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const 
   return __reduce_add_sync(0xffffffffu, c);
 }
 
-// Persistent grid; each block pulls (job, keypoint, 1024-pixel tile) items from a global counter.
-//   * the block turns the tile's pixels into 6 filter coefficients each (shared memory, 24 B/pixel);
-//   * warp w owns pixels [w*128, w*128+128) of the tile and sweeps the hypotheses in groups of 32*H:
-//     every lane keeps H hypotheses and their 2*H private vote counters in registers, the pixel
-//     coefficients arrive as broadcast LDS.128 + LDS.64 — no shuffles, ballots or atomics in the loop;
-//   * inlier <=> sign bit of t_lo = |p| - a (NaN and +0 count as "not inlier"), the second counter
-//     counts t_hi = t_lo - kappa |p|; a hypothesis whose two counters differ met an uncertain unit
-//     and is re-counted with the exact predicate.
-template <int H>
-__global__ void __launch_bounds__(kScoreThreads) k_score(ScoreArgs a) {
-  __shared__ float4 sA[kScoreTile];  // (cx, cy, D, -E)
-  __shared__ float2 sB[kScoreTile];  // (-G, -H)
-  __shared__ int s_item;
-  __shared__ int s_weird;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// upper bound of sqrt(x^2 + y^2):  max + (sqrt2 - 1) min  (exact at 0 and 45 degrees, concave in between)
+__device__ __forceinline__ float oct_norm(float x, float y) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  return fmaf(0.4142136f, fminf(ax, ay), fmaxf(ax, ay)) * 1.0000005f;
+}
+
+// Stage 2 of the filter for ONE hypothesis of a flagged pair: every lane re-evaluates its pixels of
+// the chunk from the shared-memory coefficients with the per-unit band
+//     |t| < kappa |p| + E        (E = evaluation-error bound of this hypothesis in this chunk)
+// and only units inside it are decided by exact_inlier().  Returns the correction to the sign count.
+__device__ __forceinline__ int band_adjust(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
+                                           float hxl, float hyl, float e_abs, float kappa2, float2 htrue,
+                                           const uint32_t* __restrict__ pix, const float* __restrict__ vimg, int w,
+                                           int vn, int v, int t0, float thr, unsigned long long* stats) {
+  const int lane = threadIdx.x & 31;
+  int delta = 0;
+  for (int q = lane; q < npx; q += 32) {
+    const float4 A = cA[q];
+    const float2 B = cB[q];
+    const float p = fmaf(A.x, hyl, fmaf(A.y, hxl, A.z));
+    const float t = fabsf(p) + fmaf(B.x, hxl, fmaf(B.y, hyl, A.w));
+    if (fabsf(t) < fmaf(kappa2, fabsf(p), e_abs)) {  // ~1e-5 of the units
+      const uint32_t pk = pix[t0 + q];
+      const int x = pk & 0xFFFFu, y = pk >> 16;
+      const float2 dv = load_dir(vimg, w, vn, x, y, v);
+      const bool ex = exact_inlier(htrue.x, htrue.y, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y,
+                                   exact_norm(dv.x, dv.y), thr);
+      delta += (ex ? 1 : 0) - (int)(__float_as_uint(t) >> 31);
+      if (stats) atomicAdd(&stats[1], 1ull);
+    }
+  }
+  return __reduce_add_sync(0xffffffffu, delta);
+}
+
+// K3 — THE HOT KERNEL.  Persistent grid of independent warps; each warp pulls (job, keypoint,
+// 128-pixel chunk) items from a global counter.  No block barriers.
+//
+//  * chunk-local coordinates: o = centre of the chunk's bounding box, c' = c - o (exact, one
+//    fractional bit), h' = fl(h - o) once per (hypothesis, chunk);
+//  * per pixel 6 coefficients in warp-private shared memory (24 B, broadcast LDS.128 + LDS.64):
+//        p = D hy' - E hx' - P0          (= d^ x (h - c))
+//        s = A0 - G hx' - H hy'          (= -k_lo d^ . (h - c))
+//        t = |p| + s                     inlier <=> sign(t)
+//    5 FP32-pipe instructions + 1 LEA.HI (sign count) + 1/2 FMNMX3 per unit;
+//  * every lane owns 8 hypotheses and their private counters (no shuffles/ballots/atomics in the loop);
+//  * min |t| per hypothesis pair is compared with B = c1 (|h'| + R): if min|t| >= B every sign in the
+//    chunk is provably the reference's verdict (predicate.cuh / DESIGN.md); otherwise band_adjust()
+//    finds the (rare) units that need the exact predicate.
+template <int MINB>
+__global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
+  __shared__ float4 sA[kScoreWarps][kChunk];  // (D, -E, -P0, A0)
+  __shared__ float2 sB[kScoreWarps][kChunk];  // (-G, -H)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hn = a.d.hn;
   const int n_items = a.ws.ctrl[CTRL_NITEMS];
-  const float nkappa = -a.fc.kappa;
-  const int n_groups = (hn + 32 * H - 1) / (32 * H);
+  const int n_groups = (hn + 32 * kHypPerLane - 1) / (32 * kHypPerLane);
+  float4* cA = sA[warp];
+  float2* cB = sB[warp];
+  const float qnan = __int_as_float(0x7fc00000);
   for (;;) {
-    __syncthreads();  // previous item fully consumed
-    if (tid == 0) {
-      s_item = atomicAdd(&a.ws.ctrl[CTRL_WORK], 1);
-      s_weird = 0;
-    }
-    __syncthreads();
-    const int item = s_item;
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&a.ws.ctrl[CTRL_WORK], 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
     const int2 it = a.ws.items[item];
-    const int job = it.x, v = it.y >> 20, tile = it.y & 0xFFFFF;
+    const int job = it.x, v = it.y >> 24, chunk = it.y & 0xFFFFFF;
     const int img = job / a.d.oc;
     const int tn = a.ws.job_tn[job];
     const uint32_t* pix = a.ws.pix + (size_t)img * a.d.cap + a.ws.job_off[job];
     const float* vimg = a.vertex + (size_t)img * a.d.hw * a.d.vn * 2;
-    const int tile0 = tile * kScoreTile;
+    const int t0 = chunk * kChunk;
+    const int npx = min(kChunk, tn - t0);
 
-    bool weird = false;
+    // pixels of the chunk (4 per lane), bounding box, origin
+    int px[kChunk / 32], py[kChunk / 32];
+    float2 dvs[kChunk / 32];
+    int xmin = 0x7fffffff, xmax = 0, ymin = 0x7fffffff, ymax = 0;
 #pragma unroll
-    for (int i = tid; i < kScoreTile; i += kScoreThreads) {
-      PixCoef pc;
-      pc.cx = pc.cy = pc.D = pc.E = pc.G = pc.H = 0.f;
-      const int t = tile0 + i;
-      if (t < tn) {
-        const uint32_t pk = pix[t];
-        const int x = pk & 0xFFFFu, y = pk >> 16;
-        const float2 dv = load_dir(vimg, a.d.w, a.d.vn, x, y, v);
-        weird |= !make_coef((float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y, a.fc.k_lo, pc);
+    for (int k = 0; k < kChunk / 32; ++k) {
+      const int q = k * 32 + lane;
+      px[k] = py[k] = -1;
+      dvs[k] = make_float2(0.f, 0.f);
+      if (q < npx) {
+        const uint32_t pk = pix[t0 + q];
+        px[k] = pk & 0xFFFFu;
+        py[k] = pk >> 16;
+        dvs[k] = load_dir(vimg, a.d.w, a.d.vn, px[k], py[k], v);
+        xmin = min(xmin, px[k]); xmax = max(xmax, px[k]);
+        ymin = min(ymin, py[k]); ymax = max(ymax, py[k]);
       }
-      sA[i] = make_float4(pc.cx, pc.cy, pc.D, -pc.E);
-      sB[i] = make_float2(-pc.G, -pc.H);
     }
-    if (weird) s_weird = 1;
-    __syncthreads();
-    const bool exact_tile = (a.fc.fast_ok == 0) || (s_weird != 0);
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+    const float ox = 0.5f * (float)(xmin + xmax) + 0.5f;  // exact: at most one fractional bit
+    const float oy = 0.5f * (float)(ymin + ymax) + 0.5f;
 
-    const int t0 = tile0 + warp * kPxPerWarp;        // this warp's pixel subset
-    const int npx = min(kPxPerWarp, tn - t0);        // warp-uniform; <= 0 -> nothing to do
-    if (npx <= 0) continue;
+    __syncwarp();  // previous item's readers are done with cA / cB
+    bool weird = false;
+    float rr = 0.f;
+#pragma unroll
+    for (int k = 0; k < kChunk / 32; ++k) {
+      const int q = k * 32 + lane;
+      float4 A = make_float4(0.f, 0.f, 0.f, 1.0e30f);  // invalid / padding pixel: t = +1e30, never inlier, never flagged
+      float2 B = make_float2(0.f, 0.f);
+      if (px[k] >= 0) {
+        PixCoef pc;
+        weird |= !make_coef(0.f, 0.f, dvs[k].x, dvs[k].y, a.fc.k_lo, pc);
+        const float cxl = ((float)px[k] + 0.5f) - ox, cyl = ((float)py[k] + 0.5f) - oy;  // c' = c - o, exact
+        rr = fmaxf(rr, oct_norm(cxl, cyl));
+        if (pc.D != 0.f || pc.E != 0.f) {
+          A = make_float4(pc.D, -pc.E, -(pc.D * cyl - pc.E * cxl), pc.G * cxl + pc.H * cyl);
+          B = make_float2(-pc.G, -pc.H);
+        }
+      }
+      cA[q] = A;
+      cB[q] = B;
+    }
+    rr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(rr)));  // non-negative floats order like uints
+    weird = __any_sync(0xffffffffu, weird);
+    __syncwarp();
+
     const size_t hoff = ((size_t)job * a.d.vn + v) * hn;
     int* gc = a.ws.counts + hoff;
     const float2* htrue = a.ws.hyp_true + hoff;
-
-    if (exact_tile) {
+    if (a.fc.fast_ok == 0 || weird) {  // rare: whole chunk with the exact predicate
       for (int h = 0; h < hn; ++h) {
         const float2 hp = htrue[h];
         const int c = exact_count(pix, vimg, a.d.w, a.d.vn, v, t0, npx, hp.x, hp.y, a.fc.thr);
         if (lane == 0 && c) atomicAdd(&gc[h], c);
       }
-      if (a.ws.stats && lane == 0) atomicAdd(&a.ws.stats[3], 1ull);
+      if (a.ws.stats && lane == 0) atomicAdd(&a.ws.stats[1], (unsigned long long)npx * hn);
       continue;
     }
 
     const float2* hfilt = a.ws.hyp_filt + hoff;
-    const float4* cA = sA + warp * kPxPerWarp;
-    const float2* cB = sB + warp * kPxPerWarp;
     for (int g = 0; g < n_groups; ++g) {
-      float hx[H], hy[H];
-      unsigned nlo[H], nhi[H];
+      float hx[kHypPerLane], hy[kHypPerLane], mn[kHypPerLane / 2];
+      unsigned nlo[kHypPerLane];
 #pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const int h = (g * H + i) * 32 + lane;
-        float2 hp = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+      for (int i = 0; i < kHypPerLane; ++i) {
+        const int h = (g * kHypPerLane + i) * 32 + lane;
+        float2 hp = make_float2(qnan, qnan);
         if (h < hn) hp = hfilt[h];
-        hx[i] = hp.x;
-        hy[i] = hp.y;
+        hx[i] = hp.x - ox;  // h' = fl(h - o)
+        hy[i] = hp.y - oy;
         nlo[i] = 0u;
-        nhi[i] = 0u;
       }
+#pragma unroll
+      for (int i = 0; i < kHypPerLane / 2; ++i) mn[i] = 3.0e38f;
 #pragma unroll 2
       for (int q = 0; q < npx; ++q) {
         const float4 A = cA[q];
         const float2 B = cB[q];
 #pragma unroll
-        for (int i = 0; i < H; ++i) {
-          const float hdx = hx[i] - A.x;  // the reference's rounded difference (:236)
-          const float hdy = hy[i] - A.y;
-          const float pv = fmaf(A.z, hdy, __fmul_rn(A.w, hdx));            // d^ x hd
-          const float tlo = fmaf(B.x, hdx, fmaf(B.y, hdy, fabsf(pv)));      // |p| - k_lo d^.hd
-          const float thi = fmaf(nkappa, fabsf(pv), tlo);                   // |p|/rho - k_lo d^.hd
-          nlo[i] += __float_as_uint(tlo) >> 31;
-          nhi[i] += __float_as_uint(thi) >> 31;
+        for (int i = 0; i < kHypPerLane; i += 2) {
+          const float p0 = fmaf(A.x, hy[i], fmaf(A.y, hx[i], A.z));
+          const float p1 = fmaf(A.x, hy[i + 1], fmaf(A.y, hx[i + 1], A.z));
+          const float s0 = fmaf(B.x, hx[i], fmaf(B.y, hy[i], A.w));
+          const float s1 = fmaf(B.x, hx[i + 1], fmaf(B.y, hy[i + 1], A.w));
+          const float t0v = fabsf(p0) + s0;
+          const float t1v = fabsf(p1) + s1;
+          nlo[i] += __float_as_uint(t0v) >> 31;
+          nlo[i + 1] += __float_as_uint(t1v) >> 31;
+          mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t0v)), fabsf(t1v));
         }
       }
-      // hypotheses that met an uncertain unit: exact re-count over this warp's pixels
+      // pairs whose closest unit is inside the uncertainty bound: stage 2
 #pragma unroll
-      for (int i = 0; i < H; ++i) {
-        unsigned m = __ballot_sync(0xffffffffu, nlo[i] != nhi[i]);
+      for (int i = 0; i < kHypPerLane; i += 2) {
+        const float na = oct_norm(hx[i], hy[i]) + rr, nb = oct_norm(hx[i + 1], hy[i + 1]) + rr;
+        unsigned m = __ballot_sync(0xffffffffu, mn[i >> 1] < a.fc.c1 * fmaxf(na, nb));  // NaN compares false
         while (m) {
           const int src = __ffs(m) - 1;
           m &= m - 1;
-          const float bx = __shfl_sync(0xffffffffu, hx[i], src);
-          const float by = __shfl_sync(0xffffffffu, hy[i], src);
-          const int c = exact_count(pix, vimg, a.d.w, a.d.vn, v, t0, npx, bx, by, a.fc.thr);
-          if (lane == src) nlo[i] = (unsigned)c;
-          if (a.ws.stats && lane == 0) atomicAdd(&a.ws.stats[1], (unsigned long long)npx);
+          const int hbase = (g * kHypPerLane + i) * 32 + src;
+          const float ax = __shfl_sync(0xffffffffu, hx[i], src), ay = __shfl_sync(0xffffffffu, hy[i], src);
+          const float bx = __shfl_sync(0xffffffffu, hx[i + 1], src), by = __shfl_sync(0xffffffffu, hy[i + 1], src);
+          const float ea = a.fc.e1 * __shfl_sync(0xffffffffu, na, src), eb = a.fc.e1 * __shfl_sync(0xffffffffu, nb, src);
+          const int da = band_adjust(cA, cB, npx, ax, ay, ea, a.fc.kappa2, hfilt[hbase], pix, vimg, a.d.w, a.d.vn, v, t0,
+                                     a.fc.thr, a.ws.stats);
+          int db = 0;
+          if (bx == bx)  // second hypothesis of the pair exists and is a filter hypothesis
+            db = band_adjust(cA, cB, npx, bx, by, eb, a.fc.kappa2, hfilt[hbase + 32], pix, vimg, a.d.w, a.d.vn, v, t0,
+                             a.fc.thr, a.ws.stats);
+          if (lane == src) {
+            nlo[i] += (unsigned)da;
+            nlo[i + 1] += (unsigned)db;
+          }
+          if (a.ws.stats && lane == 0) atomicAdd(&a.ws.stats[3], 1ull);
         }
       }
 #pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const int h = (g * H + i) * 32 + lane;
+      for (int i = 0; i < kHypPerLane; ++i) {
+        const int h = (g * kHypPerLane + i) * 32 + lane;
         if (h < hn && nlo[i]) atomicAdd(&gc[h], (int)nlo[i]);
       }
     }

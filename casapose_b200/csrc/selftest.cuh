@@ -46,10 +46,115 @@ __global__ void __launch_bounds__(256) k_selftest_filter(unsigned long long n, u
   atomicAdd(&out[3], inl);
 }
 
+// Scoring-loop instruction mixes for design exploration (8 hypotheses per lane, one pixel per step).
+//   PACK: 0 scalar, 1 hd as FADD2, 2 hd as FADD2 and p as FMUL2+FFMA2
+//   UNC : 0 thi FFMA + second LEA.HI counter, 1 w = |tlo| - kappa|p| + FMNMX3 per pair, 2 FMNMX3 of |tlo| per pair
+template <int PACK, int UNC>
+__device__ __forceinline__ unsigned mix_loop(int iters, float a, float b) {
+  float2 hx2[4], hy2[4];
+  unsigned nlo[8], nhi[8];
+  float mn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hx2[i] = make_float2(a * (float)(2 * i + 1), a * (float)(2 * i + 2));
+    hy2[i] = make_float2(b + (float)(2 * i), b + (float)(2 * i + 1));
+    mn[i] = 3.0e38f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) nlo[i] = nhi[i] = 0u;
+  float cx = a, cy = b;
+  const float D = 0.6f, nE = -0.8f, nG = -0.08f, nH = -0.11f, nk = -1e-4f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float2 ncx2 = make_float2(-cx, -cx), ncy2 = make_float2(-cy, -cy);
+      const float2 D2 = make_float2(D + cx, D + cx), nE2 = make_float2(nE + cy, nE + cy);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 hdx, hdy, pv;
+        if (PACK >= 1) {
+          hdx = __fadd2_rn(hx2[i], ncx2);
+          hdy = __fadd2_rn(hy2[i], ncy2);
+        } else {
+          hdx = make_float2(hx2[i].x - cx, hx2[i].y - cx);
+          hdy = make_float2(hy2[i].x - cy, hy2[i].y - cy);
+        }
+        if (PACK >= 2) {
+          pv = __ffma2_rn(D2, hdy, __fmul2_rn(nE2, hdx));
+        } else {
+          pv.x = fmaf(D2.x, hdy.x, __fmul_rn(nE2.x, hdx.x));
+          pv.y = fmaf(D2.x, hdy.y, __fmul_rn(nE2.x, hdx.y));
+        }
+        const float tla = fmaf(nG, hdx.x, fmaf(nH, hdy.x, fabsf(pv.x)));
+        const float tlb = fmaf(nG, hdx.y, fmaf(nH, hdy.y, fabsf(pv.y)));
+        nlo[2 * i] += __float_as_uint(tla) >> 31;
+        nlo[2 * i + 1] += __float_as_uint(tlb) >> 31;
+        if (UNC == 0) {
+          nhi[2 * i] += __float_as_uint(fmaf(nk, fabsf(pv.x), tla)) >> 31;
+          nhi[2 * i + 1] += __float_as_uint(fmaf(nk, fabsf(pv.y), tlb)) >> 31;
+        } else if (UNC == 1) {
+          mn[i] = fminf(fminf(mn[i], fmaf(nk, fabsf(pv.x), fabsf(tla))), fmaf(nk, fabsf(pv.y), fabsf(tlb)));
+        } else {
+          mn[i] = fminf(fminf(mn[i], fabsf(tla)), fabsf(tlb));
+        }
+      }
+      cx += 0.25f;
+      cy -= 0.125f;
+    }
+  }
+  unsigned tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += nlo[i] + 3u * nhi[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tot += __float_as_uint(mn[i]);
+  return tot;
+}
+
+// The shipped k_score inner loop (chunk-local form): 4 FFMA + FADD + LEA.HI + 1/2 FMNMX3 per unit.
+__device__ __forceinline__ unsigned mix_shipped(int iters, float a, float b) {
+  float hx[8], hy[8], mn[4];
+  unsigned nlo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hx[i] = a * (float)(i + 1);
+    hy[i] = b + (float)i;
+    nlo[i] = 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) mn[i] = 3.0e38f;
+  float4 A = make_float4(0.6f, -0.8f, a, b);
+  float2 B = make_float2(-0.08f, -0.11f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const float p0 = fmaf(A.x, hy[i], fmaf(A.y, hx[i], A.z));
+        const float p1 = fmaf(A.x, hy[i + 1], fmaf(A.y, hx[i + 1], A.z));
+        const float s0 = fmaf(B.x, hx[i], fmaf(B.y, hy[i], A.w));
+        const float s1 = fmaf(B.x, hx[i + 1], fmaf(B.y, hy[i + 1], A.w));
+        const float t0v = fabsf(p0) + s0;
+        const float t1v = fabsf(p1) + s1;
+        nlo[i] += __float_as_uint(t0v) >> 31;
+        nlo[i + 1] += __float_as_uint(t1v) >> 31;
+        mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t0v)), fabsf(t1v));
+      }
+      A.z += 0.25f;
+      A.w -= 0.125f;
+    }
+  }
+  unsigned tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += nlo[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tot += __float_as_uint(mn[i]);
+  return tot;
+}
+
 // VARIANT 0: FFMA, 16 independent chains, 2 shared operands
 // VARIANT 1: FFMA2 (fma.rn.f32x2), 8 independent float2 chains
 // VARIANT 2: FFMA with three distinct register operands per instruction
-// VARIANT 3: the instruction mix of the scoring loop (7 FP32-pipe + 2 LEA.HI per unit), counts 11 FLOP per unit
+// VARIANT 3: the scoring loop as shipped; VARIANT 10+PACK*3+UNC: exploration mixes (mix_loop)
 template <int VARIANT>
 __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float seedv) {
   const float a = 1.0f + seedv * (float)threadIdx.x, b = seedv;
@@ -90,35 +195,10 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float s
     }
 #pragma unroll
     for (int k = 0; k < 16; ++k) r += acc[k];
+  } else if (VARIANT == 3) {
+    r = __uint_as_float(mix_shipped(iters, a, b));
   } else {
-    // the scoring loop: 8 hypotheses in registers, one pixel per iteration (7 FP32-pipe + 2 LEA.HI per unit)
-    float hx[8], hy[8];
-    unsigned nlo[8], nhi[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      hx[i] = a * (float)(i + 1);
-      hy[i] = b + (float)i;
-      nlo[i] = nhi[i] = 0u;
-    }
-    float cx = a, cy = b;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float tlo, thi;
-          filter_unit(cx, cy, 0.6f, -0.8f, -0.08f, -0.11f, -1e-4f, hx[i], hy[i], tlo, thi);
-          nlo[i] += __float_as_uint(tlo) >> 31;
-          nhi[i] += __float_as_uint(thi) >> 31;
-        }
-        cx += 0.25f;
-        cy -= 0.125f;
-      }
-    }
-    unsigned tot = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tot += nlo[i] + 3u * nhi[i];
-    r = __uint_as_float(tot);
+    r = __uint_as_float(mix_loop<(VARIANT - 10) / 3, (VARIANT - 10) % 3>(iters, a, b));
   }
   if (__float_as_uint(r) == 0x7f123456u) out[0] = r;  // keep the work alive
 }

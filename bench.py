@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the keypoint-voting hot path (BASELINE.json metric: keypoint-voting frames/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (ransac_voting_layer_all_masks: mask compaction -> hypothesis
+generation -> inlier scoring -> refinement) over one batch of synthetic LM-O-shaped frames.
+Workload at every N: BASELINE config 2 per GPU — batch 16, 480x640, 8 objects x 9 keypoints, 512
+hypotheses per round (weak scaling: every rank owns its own 16 frames; the [16,8,9,2] keypoints of all
+ranks are all-gathered with NCCL inside the timed step).
+
+  value    frames/s, inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
+  e2e      frames/s through the host-buffer C-ABI entry point (pinned host -> device copy of mask and
+           vertex field, voting, device -> host copy of the keypoints, all inside the timed region)
+  roofline the scoring kernel k_score against the FP32 FMA issue rate measured in this same run
+           (FFMA micro-kernel of the library); algorithmic work = 11 FLOP per (hypothesis, pixel,
+           keypoint) test
+  cpu_baseline  the torch-CPU restatement of the reference (oracle/ransac_voting_torch.py) on a bounded
+           sample; `--impl reference` times the same restatement as its own arm.  The reference itself
+           (TensorFlow 2.9.1) cannot be installed in this image: every "reference" number here is the
+           CPU restatement of the reference, never reference TF.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, OC, VN, HN, BATCH = 480, 640, 8, 9, 512, 16
+FLOP_PER_UNIT = 11
+METRIC = "keypoint-voting frames/s (480x640, 8 obj x 9 kp, 512 hyp)"
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch on this workload,
+# from profiles/r01_k_score_full.txt (ncu --set full); null until a capture exists
+K_SCORE_DRAM_BYTES = 56.3e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--variant", default="easy")
+    ap.add_argument("--cpu-sample-frames", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.005)
+        except Exception as e:  # NVML missing: report it, do not fake numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_batch(batch, rank, variant):
+    from casapose_b200 import synthetic
+
+    return synthetic.make_frames(batch, H, W, synthetic.CONFIG_8_IDS, seed=synthetic.SEED_BASE + 1000 * rank, variant=variant)
+
+
+def cpu_restatement(d, frames, steps=1, warmup=0):
+    """Times the torch-CPU restatement of the reference on the first `frames` frames; returns (frames/s, info)."""
+    import torch
+
+    from oracle import ransac_voting_torch as T
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    mask = torch.from_numpy(d["mask"][:frames])
+    vertex = torch.from_numpy(d["vertex"][:frames])
+    times, units = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, infos = T.ransac_voting_layer_all_masks(mask, vertex, HN, seed=it, return_info=True)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            units = sum(i["units"] for i in infos)
+    mean = sum(times) / len(times)
+    return frames / mean, {"seconds_per_step": mean, "units_per_step": units, "cores": torch.get_num_threads()}
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU restatement of the reference on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = make_batch(max(args.cpu_sample_frames, 1), 0, args.variant)
+    frames = args.cpu_sample_frames
+    fps, info = cpu_restatement(d, frames, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
+    sample = "%d of the %d frames of one batch per step (all 8 classes, hn=512, same Philox hypothesis indices)" % (frames, args.batch)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config 2: keypoint voting only, 480x640, 8 objects x 9 keypoints, 512 hypotheses",
+                   "frames_per_step": frames, "note": "CPU restatement of the reference (torch-CPU, materialised [hn,tn,vn] temporaries); TensorFlow 2.9.1 is not installable in this image"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from casapose_b200 import _lib
+    from casapose_b200.pose_estimation.ransac_voting import (ransac_voting_layer_all_masks,
+                                                               ransac_voting_layer_all_masks_host)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the voting path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    if _lib._sources_newer_than_lib():
+        if rank == 0:
+            _lib.build()
+        if distributed:
+            dist.barrier()
+
+    B = args.batch
+    d = make_batch(B, rank, args.variant)
+    mask_h = torch.from_numpy(d["mask"]).pin_memory()
+    vertex_h = torch.from_numpy(d["vertex"]).pin_memory()
+    mask = mask_h.to(dev, non_blocking=True)
+    vertex = vertex_h.to(dev, non_blocking=True)
+    gathered = torch.empty((world * B, OC, VN, 2), dtype=torch.float32, device=dev)
+    lib = _lib.lib()
+    hdl = _lib.handle(local)
+    in_bytes = mask.numel() * 4 + vertex.numel() * 4
+
+    def step(seed):
+        pts = ransac_voting_layer_all_masks(mask, vertex, HN, seed=seed, image_offset=rank * B)
+        if distributed:
+            dist.all_gather_into_tensor(gathered, pts)
+            return gathered
+        return pts
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- FP32 peak of this GPU, measured in this run (roofline denominator)
+    tf, ms = C.c_double(), C.c_double()
+    _lib.check(lib.casa_measure_fp32_peak(hdl, 0, C.byref(tf), C.byref(ms)))
+    fp32_peak = tf.value
+
+    for it in range(max(args.warmup, 3)):
+        step(it)
+    barrier()
+
+    # --- timed region: K steps, device-resident inputs (510 MB per step > 126 MB L2)
+    _lib.check(lib.casa_set_timing(hdl, 1))
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    score_ms, score_launches, launches, units, exact_units = 0.0, 0, 0, 0, 0
+    barrier()
+    e0.record()
+    for it in range(args.steps):
+        step(1000 + it)
+        sm, sl, st = C.c_double(), C.c_int64(), (C.c_uint64 * 4)()
+        lib.casa_get_timing(hdl, C.byref(sm), C.byref(sl), st)
+        nl = C.c_int64()
+        lib.casa_last_launches(hdl, C.byref(nl))
+        score_ms += sm.value
+        score_launches += sl.value
+        launches += nl.value
+        units += st[0]
+        exact_units += st[1]
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    _lib.check(lib.casa_set_timing(hdl, 0))
+    elapsed_ms = e0.elapsed_time(e1)
+    if distributed:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # --- end to end through the host-buffer C-ABI entry point (pinned host buffers)
+    out_h = torch.empty((B, OC, VN, 2), dtype=torch.float32).pin_memory()
+    for it in range(2):
+        ransac_voting_layer_all_masks_host(mask_h, vertex_h, HN, seed=it, image_offset=rank * B, device=local, out=out_h)
+    barrier()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        ransac_voting_layer_all_masks_host(mask_h, vertex_h, HN, seed=2000 + it, image_offset=rank * B, device=local, out=out_h)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * B * args.steps / e2e_s
+
+    if rank == 0:
+        sum_tn = float(d["mask"].sum())
+        achieved = FLOP_PER_UNIT * units / (score_ms * 1e-3) / 1e12 if score_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "config 2: keypoint voting only, batch %d synthetic 480x640 mask + 18-ch vector field, 8 objects x 9 keypoints, 512 hypotheses, per GPU" % B,
+                "variant": args.variant, "masked_pixels_per_frame": sum_tn / B,
+                "units_per_step": units / max(args.steps, 1), "flop_per_unit": FLOP_PER_UNIT,
+                "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush needed" % (in_bytes / 1e6),
+                "parallelism": "images sharded across ranks, NCCL all-gather of [b,8,9,2] keypoints" if distributed else "single GPU",
+                "exact_fallback_fraction": exact_units / units if units else None,
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * OC * VN * 2 * 4,
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "fp32", "kernel": "k_score", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp32_peak if achieved else None, "traffic": K_SCORE_DRAM_BYTES,
+                "peak_source": "FFMA micro-kernel of this library measured in this run (MEASURED_PEAKS.json has no FP32 figure); nominal 74.5 TFLOP/s at 1965 MHz",
+                "launch_ms": score_ms / score_launches if score_launches else None,
+                "share_of_step": score_ms / elapsed_ms if elapsed_ms else None,
+            },
+        }
+        if not args.no_cpu_baseline:
+            fps, info = cpu_restatement(d, args.cpu_sample_frames)
+            line["cpu_baseline"] = {
+                "value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port",
+                "sample": "%d of the %d frames of the batch, all 8 classes, hn=512, same Philox hypothesis indices; %.1f s of CPU work" % (
+                    args.cpu_sample_frames, B, info["seconds_per_step"]),
+            }
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,11 @@ struct casa_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t last_status = 0;
   int64_t last_launches = 0;
+  int timing = 0;
+  double score_ms = 0.0;
+  int64_t score_launches = 0;
+  uint64_t stats[4] = {0, 0, 0, 0};
+  unsigned long long* pinned_stats = nullptr;  // 4 words, page-locked
   int score_p = 3;  // min resident blocks/SM the scoring kernel is compiled for (3: 80 regs, 4: 64 regs)
 };
 
@@ -63,6 +68,7 @@ extern "C" int casa_create(int device, casa_handle** out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaHostAlloc((void**)&h->pinned, CTRL_WORDS * sizeof(int), cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc((void**)&h->pinned_stats, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
@@ -78,6 +84,7 @@ extern "C" int casa_destroy(casa_handle* h) {
   if (h->ws_mem) cudaFree(h->ws_mem);
   if (h->io_mem) cudaFree(h->io_mem);
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->pinned_stats) cudaFreeHost(h->pinned_stats);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -93,7 +100,7 @@ struct Layout {
   Dims d;
   size_t off_bits, off_tile_cnt, off_tile_base, off_pix, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
       off_job_rounds, off_job_selthr, off_win_ratio, off_win_pts, off_hyp_true, off_hyp_filt, off_exact_list,
-      off_n_exact, off_counts, off_items, off_ctrl, off_sums, off_stats, total;
+      off_n_exact, off_counts, off_item_start, off_rtile_start, off_ctrl, off_partial, off_stats, total;
 };
 
 size_t bump(size_t& cur, size_t bytes) {
@@ -121,11 +128,11 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   d.J = p->b * p->oc;
   d.nct = (d.hw + kCountTile - 1) / kCountTile;
   d.cap = p->pix_capacity > 0 ? p->pix_capacity : d.hw;
-  const int tile = kChunk;
+  const long long rtiles = (long long)d.b * ((long long)d.cap / kRefineTile + d.oc + 1);
+  if (rtiles > (1ll << 30) || (long long)d.b * ((long long)d.cap / kChunk + d.oc + 1) * d.vn > (1ll << 30))
+    return fail(CASA_ERR_INVALID, "too many work items");
+  d.max_rtiles = (int)rtiles;
   (void)score_p;
-  const long long items = (long long)d.b * ((long long)d.cap / tile + d.oc + 1) * d.vn;
-  if (items > (1ll << 30)) return fail(CASA_ERR_INVALID, "too many work items");
-  d.max_items = (int)items;
   d.image_offset = p->image_offset;
   d.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFull);
   d.seed_hi = (uint32_t)(p->seed >> 32);
@@ -150,9 +157,10 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   L.off_exact_list = bump(cur, jvh * 4);
   L.off_n_exact = bump(cur, jv * 4);
   L.off_counts = bump(cur, jvh * 4);
-  L.off_items = bump(cur, (size_t)d.max_items * 8);
+  L.off_item_start = bump(cur, (J + 1) * 4);
+  L.off_rtile_start = bump(cur, (J + 1) * 4);
   L.off_ctrl = bump(cur, CTRL_WORDS * 4);
-  L.off_sums = bump(cur, jv * 5 * 8);
+  L.off_partial = bump(cur, (size_t)d.max_rtiles * d.vn * 5 * 8);
   L.off_stats = bump(cur, 4 * 8);
   L.total = cur;
   return CASA_OK;
@@ -178,9 +186,10 @@ WS make_ws(const Layout& L, void* base, bool stats) {
   w.exact_list = (int*)(b + L.off_exact_list);
   w.n_exact = (int*)(b + L.off_n_exact);
   w.counts = (int*)(b + L.off_counts);
-  w.items = (int2*)(b + L.off_items);
+  w.item_start = (int*)(b + L.off_item_start);
+  w.rtile_start = (int*)(b + L.off_rtile_start);
   w.ctrl = (int*)(b + L.off_ctrl);
-  w.sums = (double*)(b + L.off_sums);
+  w.partial = (double*)(b + L.off_partial);
   w.stats = stats ? (unsigned long long*)(b + L.off_stats) : nullptr;
   return w;
 }
@@ -234,18 +243,21 @@ extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, con
   memset(&dbg, 0, sizeof(dbg));
   if (debug) dbg = *debug;
   const Dims& d = L.d;
-  WS ws = make_ws(L, h->ws_mem, dbg.stats != nullptr);
+  WS ws = make_ws(L, h->ws_mem, true);
   const FilterConsts fc = filter_consts(p->inlier_thresh, p->force_exact);
   int64_t launches = 0;
 
   CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
-  if (ws.stats) CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
+  h->score_ms = 0.0;
+  h->score_launches = 0;
 
   const int vec4 = ((d.oc & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
   k_mask_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d, vec4);
-  k_scan_jobs<<<d.b, 256, 0, st>>>(ws, d);
+  k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
+  k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
   k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
-  launches += 3;
+  launches += 4;
   if ((float)d.hw > p->max_num) {
     k_cap_filter<<<d.J, 1024, 0, st>>>(ws, d, selection);
     ++launches;
@@ -257,23 +269,40 @@ extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, con
   sa.d = d;
   sa.fc = fc;
   sa.vertex = vertex;
+  k_init_jobs<<<(d.J + 255) / 256, 256, 0, st>>>(ws, d);
+  ++launches;
+  const int upd_threads = 32 * ((d.vn + 0) > 0 ? d.vn : 1);
   for (int rnd = 0; rnd < d.max_iter; ++rnd) {
-    k_hypgen<<<d.J, 256, 0, st>>>(ws, d, fc, vertex, idxs, rnd, dbg.hyps);
-    k_plan<<<1, 1024, 0, st>>>(ws, d, kChunk);
+    k_hypgen<<<dim3((d.hn * d.vn + 255) / 256, d.J), 256, 0, st>>>(ws, d, fc, vertex, idxs, rnd, dbg.hyps);
+    k_plan<<<1, 1024, 0, st>>>(ws, d, rnd);
     CUDA_TRY(cudaGetLastError());
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     rc = h->score_p == 4 ? launch_score<4>(h, sa, st) : launch_score<3>(h, sa, st);
     if (rc) return rc;
-    k_update<<<d.J, 256, 0, st>>>(ws, d, rnd, dbg);
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    k_update<<<d.J, upd_threads, 0, st>>>(ws, d, rnd, dbg);
     launches += 4;
     CUDA_TRY(cudaGetLastError());
     // the reference's data-dependent `while` (:318): one 32-byte read-back per round
     CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->pinned_stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    ++h->score_launches;
+    if (h->timing) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      h->score_ms += ms;
+    }
+    for (int k = 0; k < 4; ++k) h->stats[k] = h->pinned_stats[k];
     if (h->pinned[CTRL_NACTIVE] == 0) break;
   }
-  k_refine<<<dim3(d.vn, d.J), 256, 0, st>>>(ws, d, fc, vertex);
-  k_solve<<<(d.J + 127) / 128, 128, 0, st>>>(ws, d, out_points, dbg);
-  launches += 2;
+  const int n_rtiles = h->pinned[CTRL_NRTILES];  // read back with the loop's exit flag
+  if (n_rtiles > 0) {
+    k_refine<<<dim3(n_rtiles, d.vn), 256, 0, st>>>(ws, d, fc, vertex);
+    ++launches;
+  }
+  k_solve<<<d.J, 32, 0, st>>>(ws, d, out_points, dbg);
+  ++launches;
   CUDA_TRY(cudaGetLastError());
   if (dbg.pix) CUDA_TRY(cudaMemcpyAsync(dbg.pix, ws.pix, (size_t)d.b * d.cap * 4, cudaMemcpyDeviceToDevice, st));
   if (dbg.stats) CUDA_TRY(cudaMemcpyAsync(dbg.stats, ws.stats, 4 * 8, cudaMemcpyDeviceToDevice, st));
@@ -315,6 +344,21 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
 extern "C" int casa_last_status(casa_handle* h, uint32_t* status) {
   if (!h || !status) return fail(CASA_ERR_INVALID, "NULL argument");
   *status = h->last_status;
+  return CASA_OK;
+}
+
+extern "C" int casa_set_timing(casa_handle* h, int enable) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  h->timing = enable ? 1 : 0;
+  return CASA_OK;
+}
+
+extern "C" int casa_get_timing(casa_handle* h, double* score_ms, int64_t* score_launches, uint64_t* stats4) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (score_ms) *score_ms = h->score_ms;
+  if (score_launches) *score_launches = h->score_launches;
+  if (stats4)
+    for (int k = 0; k < 4; ++k) stats4[k] = h->stats[k];
   return CASA_OK;
 }
 
@@ -372,6 +416,19 @@ extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflop
       case 16: k_fma_peak<16><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       case 17: k_fma_peak<17><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       case 18: k_fma_peak<18><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 20: k_fma_peak<20><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 21: k_fma_peak<21><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 22: k_fma_peak<22><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 23: k_fma_peak<23><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 24: k_fma_peak<24><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 25: k_fma_peak<25><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 26: k_fma_peak<26><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 27: k_fma_peak<27><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 28: k_fma_peak<28><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 29: k_fma_peak<29><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 30: k_fma_peak<30><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 31: k_fma_peak<31><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 40: k_fma_peak<40><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       default: return fail(CASA_ERR_INVALID, "unknown fp32 peak variant %d", variant);
     }
     CUDA_TRY(cudaEventRecord(h->ev1, 0));

@@ -10,6 +10,8 @@ namespace casa {
 constexpr int kCountTile = 1024;   // pixels per block in the mask / scatter kernels (256 thr x 4)
 constexpr int kScoreWarps = 8;     // warps per scoring block
 constexpr int kScoreThreads = kScoreWarps * 32;
+constexpr int kChunk = 128;        // pixels per scoring work item (one warp)
+constexpr int kRefineTile = 1024;  // pixels per refinement block
 
 // job flag bits
 constexpr int JOB_GATED = 1;     // foreground_num < min_num  -> zeros   (ransac_voting.py:290)
@@ -22,6 +24,7 @@ constexpr int CTRL_NITEMS = 0;
 constexpr int CTRL_WORK = 1;
 constexpr int CTRL_NACTIVE = 2;
 constexpr int CTRL_STATUS = 3;
+constexpr int CTRL_NRTILES = 4;
 constexpr int CTRL_WORDS = 8;
 
 // hypothesis classes written by k_hypgen
@@ -59,15 +62,16 @@ struct WS {
   int* exact_list;     // [J][vn][hn]
   int* n_exact;        // [J][vn]
   int* counts;         // [J][vn][hn]
-  int2* items;         // [max_items]    scoring work items {job, v<<20 | tile}
+  int* item_start;     // [J+1]          exclusive prefix of scoring work items (chunks x vn) over active jobs
+  int* rtile_start;    // [J+1]          exclusive prefix of refinement tiles over live jobs
   int* ctrl;           // [CTRL_WORDS]
-  double* sums;        // [J][vn][5]     sum nx*nx, nx*ny, ny*ny, nx*b, ny*b
+  double* partial;     // [max_rtiles][vn][5]  per-tile sums nx*nx, nx*ny, ny*ny, nx*b, ny*b
   unsigned long long* stats;  // [4]
 };
 
 struct Dims {
   int b, h, w, oc, vn, hn, max_iter;
-  int hw, J, nct, cap, max_items;
+  int hw, J, nct, cap, max_rtiles;
   int image_offset;
   uint32_t seed_lo, seed_hi;
   float min_num, max_num, confidence;

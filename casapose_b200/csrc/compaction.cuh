@@ -5,8 +5,8 @@
 // pairs of the batch at once:
 //   k_mask_bits   reads the float mask ONCE (the only pass over [b,h,w,oc]), writes one
 //                 class-membership word per pixel and per-tile class counts (warp ballots);
-//   k_scan_jobs   exclusive prefix over the tiles of each (image, class), job table
-//                 (foreground_num gate :290, down-sampling threshold :298);
+//   k_scan_tiles  exclusive prefix over the tiles of each (image, class);
+//   k_job_table   class offsets, foreground_num gate (:290), down-sampling threshold (:298);
 //   k_scatter     raster-order scatter of packed pixel coordinates (y<<16 | x) — the order is
 //                 semantically required because hypothesis indices address this list (:216);
 //   k_cap_filter  in-place ordered filter  selection < max_num / foreground_num  (:295-301).
@@ -61,64 +61,63 @@ __global__ void __launch_bounds__(256) k_mask_bits(const float* __restrict__ mas
   if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
 }
 
-// one block per image
-__global__ void __launch_bounds__(256) k_scan_jobs(WS ws, Dims d) {
-  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int swarp[8];
+// one block (128 threads) per job: exclusive prefix of the job's tile counts, foreground_num (:287)
+__global__ void __launch_bounds__(128) k_scan_tiles(WS ws, Dims d) {
+  const int job = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int swarp[4];
   __shared__ int srun;
-  __shared__ int stn0[32];
-  for (int c = 0; c < d.oc; ++c) {
-    const int* cnt = ws.tile_cnt + ((size_t)img * d.oc + c) * d.nct;
-    int* base = ws.tile_base + ((size_t)img * d.oc + c) * d.nct;
-    if (tid == 0) srun = 0;
-    __syncthreads();
-    for (int s = 0; s < d.nct; s += 256) {
-      const int i = s + tid;
-      const int v = i < d.nct ? cnt[i] : 0;
-      int x = v;
+  const int* cnt = ws.tile_cnt + (size_t)job * d.nct;
+  int* base = ws.tile_base + (size_t)job * d.nct;
+  if (tid == 0) srun = 0;
+  __syncthreads();
+  for (int s = 0; s < d.nct; s += 128) {
+    const int i = s + tid;
+    const int v = i < d.nct ? cnt[i] : 0;
+    int x = v;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      if (lane == 31) swarp[warp] = x;
-      __syncthreads();
-      int woff = 0;
-      for (int k = 0; k < warp; ++k) woff += swarp[k];
-      const int run = srun;
-      if (i < d.nct) base[i] = run + woff + x - v;
-      __syncthreads();
-      if (tid == 255) srun = run + woff + x;
-      __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    if (tid == 0) stn0[c] = srun;
+    if (lane == 31) swarp[warp] = x;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < warp; ++k) woff += swarp[k];
+    const int run = srun;
+    if (i < d.nct) base[i] = run + woff + x - v;
+    __syncthreads();
+    if (tid == 127) srun = run + woff + x;
     __syncthreads();
   }
-  if (tid == 0) {
-    int off = 0;
-    for (int c = 0; c < d.oc; ++c) {
-      const int job = img * d.oc + c;
-      const int tn0 = stn0[c];
-      int flags = 0;
-      const float fg = (float)tn0;  // tf.reduce_sum of a {0,1} mask (:287)
-      if (fg < d.min_num) flags |= JOB_GATED;               // :290
-      float thr = 1.f;
-      if (fg > d.max_num) {                                 // :295
-        flags |= JOB_NEEDS_CAP;
-        thr = __fdiv_rn(d.max_num, fg);                     // :298
-      }
-      if (off + tn0 > d.cap) {
-        flags |= JOB_GATED | JOB_OVERFLOW;
-        atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_PIX_OVERFLOW);
-      }
-      ws.job_tn0[job] = tn0;
-      ws.job_tn[job] = (flags & JOB_OVERFLOW) ? 0 : tn0;
-      ws.job_off[job] = off;
-      ws.job_flags[job] = flags;
-      ws.job_rounds[job] = 0;
-      ws.job_selthr[job] = thr;
-      if (!(flags & JOB_OVERFLOW)) off += tn0;
+  if (tid == 0) ws.job_tn0[job] = srun;
+}
+
+// one thread per image: class offsets inside the image's pixel list, gate (:290), cap threshold (:298)
+__global__ void __launch_bounds__(64) k_job_table(WS ws, Dims d) {
+  const int img = blockIdx.x * 64 + threadIdx.x;
+  if (img >= d.b) return;
+  int off = 0;
+  for (int c = 0; c < d.oc; ++c) {
+    const int job = img * d.oc + c;
+    const int tn0 = ws.job_tn0[job];
+    int flags = 0;
+    const float fg = (float)tn0;  // tf.reduce_sum of a {0,1} mask (:287)
+    if (fg < d.min_num) flags |= JOB_GATED;               // :290
+    float thr = 1.f;
+    if (fg > d.max_num) {                                 // :295
+      flags |= JOB_NEEDS_CAP;
+      thr = __fdiv_rn(d.max_num, fg);                     // :298
     }
+    if (off + tn0 > d.cap) {
+      flags |= JOB_GATED | JOB_OVERFLOW;
+      atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_PIX_OVERFLOW);
+    }
+    ws.job_tn[job] = (flags & JOB_OVERFLOW) ? 0 : tn0;
+    ws.job_off[job] = off;
+    ws.job_flags[job] = flags;
+    ws.job_rounds[job] = 0;
+    ws.job_selthr[job] = thr;
+    if (!(flags & JOB_OVERFLOW)) off += tn0;
   }
 }
 

@@ -68,16 +68,21 @@ struct PixCoef {
   float G, H;    // k_lo * d^
 };
 
+// float32 bit pattern of the smallest q with sqrt_rn(q) > 1e-6f (sqrt_rn is monotone), so that
+//   tf.norm(direct) > 1e-6  (:238-240)   <=>   fl(fl(dx*dx) + fl(dy*dy)) >= kNormSqMin
+// without evaluating the square root (checked on the host: tests/test_oracle_ransac.py).
+constexpr uint32_t kNormSqMinBits = 0x2b8cbcceu;  // 1.0000002e-12f
+
 // Returns false if this (pixel, keypoint) cannot use the filter (non-finite or huge direction).
 __device__ __forceinline__ bool make_coef(float cx, float cy, float dx, float dy, float k_lo, PixCoef& c) {
   c.cx = cx;
   c.cy = cy;
-  c.D = c.E = c.G = c.H = 0.f;  // zero forms: |0| < 0 is false for lo and hi -> never an inlier
+  c.D = c.E = c.G = c.H = 0.f;  // zero forms: never an inlier
   const float ax = fabsf(dx), ay = fabsf(dy);
   if (!(ax <= kDirMax && ay <= kDirMax)) return false;  // also catches NaN / inf
-  const float nd = exact_norm(dx, dy);
-  if (nd > kEps1e6) {  // :240, decided on the exact norm
-    const float inv = 1.0f / nd;
+  const float q = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  if (q >= __uint_as_float(kNormSqMinBits)) {  // <=> exact_norm(dx,dy) > 1e-6f (:240)
+    const float inv = rsqrtf(q);               // 2 ulp; a common scale of (D,E,G,H) cannot change a sign
     c.D = dx * inv;
     c.E = dy * inv;
     c.G = k_lo * c.D;

@@ -1,14 +1,14 @@
 // K2-K4 — the RANSAC loop of ransac_voting_batch
 // (/root/reference/casapose/pose_estimation/ransac_voting.py:310-368) for every (image, class) job.
 //
-//   k_hypgen   idxs -> hypotheses, exact float32 sequence (:319-322, :197-227), classifies
-//              each hypothesis for the filtered predicate and zeroes the vote counters;
-//   k_plan     turns the active jobs into a flat list of scoring work items
-//              (job, keypoint, pixel tile) for the persistent scoring grid;
-//   k_score    THE HOT KERNEL: hypotheses x pixels inlier test (:230-249) and vote counts (:327);
-//   k_update   arg-max per keypoint (:328-333), best-so-far update (:336-338), stop test (:340-347);
-//   k_refine   re-vote of the winners and the normal-equation sums (:349-362);
-//   k_solve    invertibility test and 2x2 solve (:254-272, :364-368).
+//   k_init_jobs  loop state of every job (:310-316)
+//   k_hypgen     idxs -> hypotheses, exact float32 sequence (:319-322, :197-227), classifies each
+//                hypothesis for the filtered predicate and zeroes the vote counters
+//   k_plan       exclusive prefixes of scoring work items / refinement tiles over the jobs
+//   k_score      THE HOT KERNEL: hypotheses x pixels inlier test (:230-249) and vote counts (:327)
+//   k_update     arg-max per keypoint (:328-333), best-so-far update (:336-338), stop test (:340-347)
+//   k_refine     re-vote of the winners and per-tile normal-equation sums (:349-362)
+//   k_solve      ordered sum of the tiles, invertibility test and 2x2 solve (:254-272, :364-368)
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -22,110 +22,129 @@ __device__ __forceinline__ float2 load_dir(const float* __restrict__ vimg, int w
   return make_float2(t.y, t.x);
 }
 
+// ------------------------------------------------------------------------------------ init
+// one thread per job (round 0 only)
+__global__ void __launch_bounds__(256) k_init_jobs(WS ws, Dims d) {
+  const int job = blockIdx.x * 256 + threadIdx.x;
+  if (job >= d.J) return;
+  const int flags = ws.job_flags[job];
+  const bool act = !(flags & JOB_GATED) && ws.job_tn[job] > 0;
+  ws.job_flags[job] = act ? (flags | JOB_ACTIVE) : (flags & ~JOB_ACTIVE);
+  for (int v = 0; v < d.vn; ++v) {
+    ws.win_ratio[job * d.vn + v] = 0.f;  // :311-312
+    ws.win_pts[job * d.vn + v] = make_float2(0.f, 0.f);
+    ws.n_exact[job * d.vn + v] = 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------ K2
-// one block per job
+// grid (ceil(hn*vn/256), J): one thread per (hypothesis, keypoint) of an active job
 __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, const float* __restrict__ vertex,
                                                 const int32_t* __restrict__ idxs, int rnd, float* dbg_hyps) {
-  const int job = blockIdx.x, tid = threadIdx.x;
-  int flags = ws.job_flags[job];
+  const int job = blockIdx.y;
+  if (!(ws.job_flags[job] & JOB_ACTIVE)) return;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= d.hn * d.vn) return;
   const int tn = ws.job_tn[job];
-  if (rnd == 0) {
-    const bool act = !(flags & JOB_GATED) && tn > 0;
-    __syncthreads();  // everyone has read the old flags
-    if (tid == 0) ws.job_flags[job] = act ? (flags | JOB_ACTIVE) : (flags & ~JOB_ACTIVE);
-    for (int v = tid; v < d.vn; v += 256) {
-      ws.win_ratio[job * d.vn + v] = 0.f;  // :311-312
-      ws.win_pts[job * d.vn + v] = make_float2(0.f, 0.f);
-    }
-    if (!act) return;
-  } else if (!(flags & JOB_ACTIVE)) {
-    return;
-  }
   const int img = job / d.oc, cls = job - img * d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
   const float* vimg = vertex + (size_t)img * d.hw * d.vn * 2;
-  for (int v = tid; v < d.vn; v += 256) ws.n_exact[job * d.vn + v] = 0;
-  __syncthreads();
-  const int n = d.hn * d.vn;
-  for (int e = tid; e < n; e += 256) {
-    const int h = e / d.vn, v = e - h * d.vn;
-    int2 ip;
-    if (idxs) {
-      const int32_t* src = idxs + ((((size_t)job * d.max_iter + rnd) * d.hn + h) * d.vn + v) * 2;
-      ip = make_int2(src[0], src[1]);
-      if ((unsigned)ip.x >= (unsigned)tn || (unsigned)ip.y >= (unsigned)tn) {
-        atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_IDX_RANGE);
-        ip.x = min(max(ip.x, 0), tn - 1);
-        ip.y = min(max(ip.y, 0), tn - 1);
-      }
-    } else {
-      ip = philox_idx_pair((uint32_t)h, (uint32_t)v, (uint32_t)d.vn, (uint32_t)rnd, (uint32_t)cls,
-                           (uint32_t)(d.image_offset + img), (uint32_t)tn, d.seed_lo, d.seed_hi);
+  const int h = e / d.vn, v = e - h * d.vn;
+  int2 ip;
+  if (idxs) {
+    const int32_t* src = idxs + ((((size_t)job * d.max_iter + rnd) * d.hn + h) * d.vn + v) * 2;
+    ip = make_int2(src[0], src[1]);
+    if ((unsigned)ip.x >= (unsigned)tn || (unsigned)ip.y >= (unsigned)tn) {
+      atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_IDX_RANGE);
+      ip.x = min(max(ip.x, 0), tn - 1);
+      ip.y = min(max(ip.y, 0), tn - 1);
     }
-    const uint32_t p0 = pix[ip.x], p1 = pix[ip.y];
-    const int x0 = p0 & 0xFFFFu, y0 = p0 >> 16, x1 = p1 & 0xFFFFu, y1 = p1 >> 16;
-    const float2 c0 = make_float2((float)x0 + 0.5f, (float)y0 + 0.5f);  // :306
-    const float2 c1 = make_float2((float)x1 + 0.5f, (float)y1 + 0.5f);
-    const float2 d0 = load_dir(vimg, d.w, d.vn, x0, y0, v);
-    const float2 d1 = load_dir(vimg, d.w, d.vn, x1, y1, v);
-    const float2 hp = exact_hypothesis(c0, c1, d0, d1);
-    const size_t o = ((size_t)job * d.vn + v) * d.hn + h;
-    ws.hyp_true[o] = hp;
-    const int kind = classify_hypothesis(hp.x, hp.y, fc.fast_ok != 0);
-    const float qnan = __int_as_float(0x7fc00000);
-    ws.hyp_filt[o] = kind == 0 ? hp : make_float2(qnan, qnan);
-    if (kind == 2) {
-      const int slot = atomicAdd(&ws.n_exact[job * d.vn + v], 1);
-      ws.exact_list[((size_t)job * d.vn + v) * d.hn + slot] = h;
-      if (ws.stats) atomicAdd(&ws.stats[2], 1ull);
-    }
-    ws.counts[o] = 0;
-    if (dbg_hyps) {
-      float* dst = dbg_hyps + ((((size_t)job * d.max_iter + rnd) * d.hn + h) * d.vn + v) * 2;
-      dst[0] = hp.x;
-      dst[1] = hp.y;
-    }
+  } else {
+    ip = philox_idx_pair((uint32_t)h, (uint32_t)v, (uint32_t)d.vn, (uint32_t)rnd, (uint32_t)cls,
+                         (uint32_t)(d.image_offset + img), (uint32_t)tn, d.seed_lo, d.seed_hi);
+  }
+  const uint32_t p0 = pix[ip.x], p1 = pix[ip.y];
+  const int x0 = p0 & 0xFFFFu, y0 = p0 >> 16, x1 = p1 & 0xFFFFu, y1 = p1 >> 16;
+  const float2 c0 = make_float2((float)x0 + 0.5f, (float)y0 + 0.5f);  // :306
+  const float2 c1 = make_float2((float)x1 + 0.5f, (float)y1 + 0.5f);
+  const float2 d0 = load_dir(vimg, d.w, d.vn, x0, y0, v);
+  const float2 d1 = load_dir(vimg, d.w, d.vn, x1, y1, v);
+  const float2 hp = exact_hypothesis(c0, c1, d0, d1);
+  const size_t o = ((size_t)job * d.vn + v) * d.hn + h;
+  ws.hyp_true[o] = hp;
+  const int kind = classify_hypothesis(hp.x, hp.y, fc.fast_ok != 0);
+  const float qnan = __int_as_float(0x7fc00000);
+  ws.hyp_filt[o] = kind == 0 ? hp : make_float2(qnan, qnan);
+  if (kind == 2) {
+    const int slot = atomicAdd(&ws.n_exact[job * d.vn + v], 1);
+    ws.exact_list[((size_t)job * d.vn + v) * d.hn + slot] = h;
+    atomicAdd(&ws.stats[2], 1ull);
+  }
+  ws.counts[o] = 0;
+  if (dbg_hyps) {
+    float* dst = dbg_hyps + ((((size_t)job * d.max_iter + rnd) * d.hn + h) * d.vn + v) * 2;
+    dst[0] = hp.x;
+    dst[1] = hp.y;
   }
 }
 
 // ------------------------------------------------------------------------------------ plan
-// single block; tile_px = pixels per scoring work item
-__global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int tile_px) {
+// single block: item_start[j] = sum over active jobs j' < j of ceil(tn/128) * vn;  (round 0 only)
+// rtile_start[j] = sum over live jobs of ceil(tn/1024)
+__global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int swarp[32];
-  __shared__ int srun;
-  if (tid == 0) srun = 0;
+  __shared__ int swarp[2][32];
+  __shared__ int srun[2];
+  if (tid < 2) srun[tid] = 0;
   __syncthreads();
   for (int s = 0; s < d.J; s += 1024) {
     const int job = s + tid;
-    int nt = 0;
-    if (job < d.J && (ws.job_flags[job] & JOB_ACTIVE)) nt = (ws.job_tn[job] + tile_px - 1) / tile_px;
-    const int cnt = nt * d.vn;
-    int x = cnt;
+    int ci = 0, cr = 0;
+    if (job < d.J) {
+      const int flags = ws.job_flags[job], tn = ws.job_tn[job];
+      if (flags & JOB_ACTIVE) ci = ((tn + kChunk - 1) / kChunk) * d.vn;
+      if (!(flags & JOB_GATED) && tn > 0) cr = (tn + kRefineTile - 1) / kRefineTile;
+    }
+    int xi = ci, xr = cr;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) swarp[warp] = x;
-    __syncthreads();
-    int woff = 0;
-    for (int k = 0; k < warp; ++k) woff += swarp[k];
-    const int run = srun;
-    int pos = run + woff + x - cnt;
-    for (int t = 0; t < nt; ++t)
-      for (int v = 0; v < d.vn; ++v) {
-        if (pos < d.max_items) ws.items[pos] = make_int2(job, (v << 24) | t);
-        ++pos;
+      const int yi = __shfl_up_sync(0xffffffffu, xi, o), yr = __shfl_up_sync(0xffffffffu, xr, o);
+      if (lane >= o) {
+        xi += yi;
+        xr += yr;
       }
+    }
+    if (lane == 31) {
+      swarp[0][warp] = xi;
+      swarp[1][warp] = xr;
+    }
     __syncthreads();
-    if (tid == 1023) srun = run + woff + x;
+    int wi = 0, wr = 0;
+    for (int k = 0; k < warp; ++k) {
+      wi += swarp[0][k];
+      wr += swarp[1][k];
+    }
+    const int ri = srun[0], rr = srun[1];
+    if (job < d.J) {
+      ws.item_start[job] = ri + wi + xi - ci;
+      if (rnd == 0) ws.rtile_start[job] = rr + wr + xr - cr;
+    }
+    __syncthreads();
+    if (tid == 1023) {
+      srun[0] = ri + wi + xi;
+      srun[1] = rr + wr + xr;
+    }
     __syncthreads();
   }
   if (tid == 0) {
-    ws.ctrl[CTRL_NITEMS] = min(srun, d.max_items);
+    ws.item_start[d.J] = srun[0];
+    ws.ctrl[CTRL_NITEMS] = srun[0];
     ws.ctrl[CTRL_WORK] = 0;
     ws.ctrl[CTRL_NACTIVE] = 0;
+    if (rnd == 0) {
+      ws.rtile_start[d.J] = srun[1];
+      ws.ctrl[CTRL_NRTILES] = srun[1];
+    }
   }
 }
 
@@ -137,7 +156,6 @@ struct ScoreArgs {
   const float* vertex;
 };
 
-constexpr int kChunk = 128;  // pixels per scoring work item (one warp)
 constexpr int kHypPerLane = 8;
 
 // Exact inlier count of one hypothesis over pixels [t0, t0+npx) of a job, whole warp cooperating.
@@ -160,32 +178,46 @@ __device__ __forceinline__ float oct_norm(float x, float y) {
   return fmaf(0.4142136f, fminf(ax, ay), fmaxf(ax, ay)) * 1.0000005f;
 }
 
-// Stage 2 of the filter for ONE hypothesis of a flagged pair: every lane re-evaluates its pixels of
-// the chunk from the shared-memory coefficients with the per-unit band
-//     |t| < kappa |p| + E        (E = evaluation-error bound of this hypothesis in this chunk)
-// and only units inside it are decided by exact_inlier().  Returns the correction to the sign count.
-__device__ __forceinline__ int band_adjust(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
-                                           float hxl, float hyl, float e_abs, float kappa2, float2 htrue,
-                                           const uint32_t* __restrict__ pix, const float* __restrict__ vimg, int w,
-                                           int vn, int v, int t0, float thr, unsigned long long* stats) {
+// Stage 2 of the filter for the two hypotheses (a, b) of a flagged pair: every lane re-evaluates its
+// pixels of the chunk from the shared-memory coefficients with the per-unit band
+//     |t| < kappa |p| + E        (E = evaluation-error bound of that hypothesis in this chunk)
+// and only units inside it are decided by exact_inlier().  Returns the corrections to the two sign
+// counts.  A NaN hypothesis (no partner / not a filter hypothesis) never enters the band.
+__device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
+                                             float ax, float ay, float bx, float by, float ea, float eb, float kappa2,
+                                             const float2* __restrict__ hfilt, int ha, int hb_ok,
+                                             const uint32_t* __restrict__ pix, const float* __restrict__ vimg, int w,
+                                             int vn, int v, int t0, float thr, unsigned long long* stats) {
   const int lane = threadIdx.x & 31;
-  int delta = 0;
+  int da = 0, db = 0;
   for (int q = lane; q < npx; q += 32) {
     const float4 A = cA[q];
     const float2 B = cB[q];
-    const float p = fmaf(A.x, hyl, fmaf(A.y, hxl, A.z));
-    const float t = fabsf(p) + fmaf(B.x, hxl, fmaf(B.y, hyl, A.w));
-    if (fabsf(t) < fmaf(kappa2, fabsf(p), e_abs)) {  // ~1e-5 of the units
+    const float pa = fmaf(A.x, ay, fmaf(A.y, ax, A.z));
+    const float pb = fmaf(A.x, by, fmaf(A.y, bx, A.z));
+    const float ta = fabsf(pa) + fmaf(B.x, ax, fmaf(B.y, ay, A.w));
+    const float tb = fabsf(pb) + fmaf(B.x, bx, fmaf(B.y, by, A.w));
+    const bool ua = fabsf(ta) < fmaf(kappa2, fabsf(pa), ea);
+    const bool ub = fabsf(tb) < fmaf(kappa2, fabsf(pb), eb);
+    if (ua || ub) {  // ~1e-5 of the units
       const uint32_t pk = pix[t0 + q];
       const int x = pk & 0xFFFFu, y = pk >> 16;
       const float2 dv = load_dir(vimg, w, vn, x, y, v);
-      const bool ex = exact_inlier(htrue.x, htrue.y, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y,
-                                   exact_norm(dv.x, dv.y), thr);
-      delta += (ex ? 1 : 0) - (int)(__float_as_uint(t) >> 31);
-      if (stats) atomicAdd(&stats[1], 1ull);
+      const float nd = exact_norm(dv.x, dv.y);
+      if (ua) {
+        const float2 h = hfilt[ha];
+        da += (exact_inlier(h.x, h.y, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y, nd, thr) ? 1 : 0) -
+              (int)(__float_as_uint(ta) >> 31);
+      }
+      if (ub && hb_ok) {
+        const float2 h = hfilt[ha + 32];
+        db += (exact_inlier(h.x, h.y, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y, nd, thr) ? 1 : 0) -
+              (int)(__float_as_uint(tb) >> 31);
+      }
+      if (stats) atomicAdd(&stats[1], (unsigned long long)(ua ? 1 : 0) + (ub ? 1 : 0));
     }
   }
-  return __reduce_add_sync(0xffffffffu, delta);
+  return make_int2(__reduce_add_sync(0xffffffffu, da), __reduce_add_sync(0xffffffffu, db));
 }
 
 // K3 — THE HOT KERNEL.  Persistent grid of independent warps; each warp pulls (job, keypoint,
@@ -218,8 +250,16 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     if (lane == 0) item = atomicAdd(&a.ws.ctrl[CTRL_WORK], 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    const int2 it = a.ws.items[item];
-    const int job = it.x, v = it.y >> 24, chunk = it.y & 0xFFFFFF;
+    // item -> (job, chunk, keypoint): binary search in the per-job prefix of work items (keypoint innermost,
+    // so the 9 items that share a chunk's pixels are handed out back to back)
+    int lo = 0, hi = a.d.J;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(&a.ws.item_start[mid]) <= item) lo = mid; else hi = mid;
+    }
+    const int job = lo;
+    const int rem = item - __ldg(&a.ws.item_start[job]);
+    const int chunk = rem / a.d.vn, v = rem - chunk * a.d.vn;
     const int img = job / a.d.oc;
     const int tn = a.ws.job_tn[job];
     const uint32_t* pix = a.ws.pix + (size_t)img * a.d.cap + a.ws.job_off[job];
@@ -320,35 +360,40 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
           mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t0v)), fabsf(t1v));
         }
       }
-      // pairs whose closest unit is inside the uncertainty bound: stage 2
+      // pairs whose closest unit is inside the uncertainty bound (NaN compares false)
+      unsigned flagged = 0u;
 #pragma unroll
       for (int i = 0; i < kHypPerLane; i += 2) {
-        const float na = oct_norm(hx[i], hy[i]) + rr, nb = oct_norm(hx[i + 1], hy[i + 1]) + rr;
-        unsigned m = __ballot_sync(0xffffffffu, mn[i >> 1] < a.fc.c1 * fmaxf(na, nb));  // NaN compares false
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int hbase = (g * kHypPerLane + i) * 32 + src;
-          const float ax = __shfl_sync(0xffffffffu, hx[i], src), ay = __shfl_sync(0xffffffffu, hy[i], src);
-          const float bx = __shfl_sync(0xffffffffu, hx[i + 1], src), by = __shfl_sync(0xffffffffu, hy[i + 1], src);
-          const float ea = a.fc.e1 * __shfl_sync(0xffffffffu, na, src), eb = a.fc.e1 * __shfl_sync(0xffffffffu, nb, src);
-          const int da = band_adjust(cA, cB, npx, ax, ay, ea, a.fc.kappa2, hfilt[hbase], pix, vimg, a.d.w, a.d.vn, v, t0,
-                                     a.fc.thr, a.ws.stats);
-          int db = 0;
-          if (bx == bx)  // second hypothesis of the pair exists and is a filter hypothesis
-            db = band_adjust(cA, cB, npx, bx, by, eb, a.fc.kappa2, hfilt[hbase + 32], pix, vimg, a.d.w, a.d.vn, v, t0,
-                             a.fc.thr, a.ws.stats);
-          if (lane == src) {
-            nlo[i] += (unsigned)da;
-            nlo[i + 1] += (unsigned)db;
-          }
-          if (a.ws.stats && lane == 0) atomicAdd(&a.ws.stats[3], 1ull);
-        }
+        const float nmax = fmaxf(oct_norm(hx[i], hy[i]), oct_norm(hx[i + 1], hy[i + 1])) + rr;
+        flagged |= (mn[i >> 1] < a.fc.c1 * nmax ? 1u : 0u) << (i >> 1);
       }
 #pragma unroll
       for (int i = 0; i < kHypPerLane; ++i) {
         const int h = (g * kHypPerLane + i) * 32 + lane;
         if (h < hn && nlo[i]) atomicAdd(&gc[h], (int)nlo[i]);
+      }
+      // stage 2, after the group's registers are dead: corrections go straight to the global counters
+      if (__any_sync(0xffffffffu, flagged != 0u)) {
+        for (int i2 = 0; i2 < kHypPerLane / 2; ++i2) {
+          unsigned m = __ballot_sync(0xffffffffu, (flagged >> i2) & 1u);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int ha = (g * kHypPerLane + 2 * i2) * 32 + src;
+            const bool hb_ok = ha + 32 < hn;
+            const float2 pa = hfilt[ha];
+            const float2 pb = hb_ok ? hfilt[ha + 32] : make_float2(qnan, qnan);
+            const float ax = pa.x - ox, ay = pa.y - oy, bx = pb.x - ox, by = pb.y - oy;  // same h' as the main loop
+            const float ea = a.fc.e1 * (oct_norm(ax, ay) + rr), eb = a.fc.e1 * (oct_norm(bx, by) + rr);
+            const int2 dd = band_adjust2(cA, cB, npx, ax, ay, bx, by, ea, eb, a.fc.kappa2, hfilt, ha, hb_ok, pix, vimg,
+                                         a.d.w, a.d.vn, v, t0, a.fc.thr, a.ws.stats);
+            if (lane == 0) {
+              if (dd.x) atomicAdd(&gc[ha], dd.x);
+              if (dd.y) atomicAdd(&gc[ha + 32], dd.y);
+              atomicAdd(&a.ws.stats[3], 1ull);
+            }
+          }
+        }
       }
     }
     // hypotheses the filter cannot take (exact list)
@@ -382,18 +427,17 @@ __device__ __forceinline__ bool stop_test(float min_ratio, int hyp_num, float co
 }
 
 // ------------------------------------------------------------------------------------ K3b
-// one block per job
-__global__ void __launch_bounds__(256) k_update(WS ws, Dims d, int rnd, casa_ransac_debug dbg) {
+// one block per job, one warp per keypoint
+__global__ void __launch_bounds__(512) k_update(WS ws, Dims d, int rnd, casa_ransac_debug dbg) {
   const int job = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int flags = ws.job_flags[job];
   if (!(flags & JOB_ACTIVE)) return;
-  __shared__ unsigned long long sbest[8];
   __shared__ unsigned long long svbest[16];
   const int tn = ws.job_tn[job];
-  for (int v = 0; v < d.vn; ++v) {
-    const int* c = ws.counts + ((size_t)job * d.vn + v) * d.hn;
+  if (warp < d.vn) {
+    const int* c = ws.counts + ((size_t)job * d.vn + warp) * d.hn;
     unsigned long long best = 0ull;  // (count << 32) | ~h : max count, then lowest h (:328 argmax takes the first)
-    for (int h = tid; h < d.hn; h += 256) {
+    for (int h = lane; h < d.hn; h += 32) {
       const unsigned long long key = ((unsigned long long)(unsigned)c[h] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)h);
       best = key > best ? key : best;
     }
@@ -402,22 +446,17 @@ __global__ void __launch_bounds__(256) k_update(WS ws, Dims d, int rnd, casa_ran
       const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
       best = y > best ? y : best;
     }
-    if (lane == 0) sbest[warp] = best;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long bb = sbest[0];
-      for (int k = 1; k < 8; ++k) bb = sbest[k] > bb ? sbest[k] : bb;
-      svbest[v] = bb;
-    }
-    __syncthreads();
+    if (lane == 0) svbest[warp] = best;
   }
+  __syncthreads();
   if (dbg.counts) {
     int32_t* dst = dbg.counts + ((size_t)job * d.max_iter + rnd) * d.hn * d.vn;
-    for (int e = tid; e < d.hn * d.vn; e += 256) {
+    for (int e = tid; e < d.hn * d.vn; e += blockDim.x) {
       const int h = e / d.vn, v = e - h * d.vn;
       dst[e] = ws.counts[((size_t)job * d.vn + v) * d.hn + h];
     }
   }
+  if (tid < d.vn) ws.n_exact[job * d.vn + tid] = 0;  // for the next round's k_hypgen
   if (tid == 0) {
     float min_ratio = 3.0e38f;
     for (int v = 0; v < d.vn; ++v) {
@@ -442,36 +481,50 @@ __global__ void __launch_bounds__(256) k_update(WS ws, Dims d, int rnd, casa_ran
     } else {
       atomicAdd(&ws.ctrl[CTRL_NACTIVE], 1);
     }
-    if (ws.stats) atomicAdd(&ws.stats[0], (unsigned long long)tn * d.vn * d.hn);
+    atomicAdd(&ws.stats[0], (unsigned long long)tn * d.vn * d.hn);
   }
 }
 
 // ------------------------------------------------------------------------------------ K4
-// grid (vn, J), one block per (job, keypoint): re-vote the winner and accumulate the normal equations.
+// grid (n_rtiles, vn): one block per (1024-pixel tile of a job, keypoint); 4 pixels per thread.
+// Re-votes the winner (:353) and accumulates the normal equations (:356-362): float32 products exactly
+// as the reference forms them (normal * inlier flag, so a non-finite direction poisons the sums as it
+// does there), float64 accumulation, fixed reduction order.
 __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc, const float* __restrict__ vertex) {
-  const int v = blockIdx.x, job = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int flags = ws.job_flags[job];
+  const int rt = blockIdx.x, v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int lo = 0, hi = d.J;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (ws.rtile_start[mid] <= rt) lo = mid; else hi = mid;
+  }
+  const int job = lo, tile = rt - ws.rtile_start[job];
   const int tn = ws.job_tn[job];
-  if ((flags & JOB_GATED) || tn <= 0) return;
   const int img = job / d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
   const float* vimg = vertex + (size_t)img * d.hw * d.vn * 2;
   const float2 wp = ws.win_pts[job * d.vn + v];
   double s[5] = {0, 0, 0, 0, 0};
-  for (int t = tid; t < tn; t += 256) {
-    const uint32_t pk = pix[t];
-    const int x = pk & 0xFFFFu, y = pk >> 16;
-    const float2 dv = load_dir(vimg, d.w, d.vn, x, y, v);
-    const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
-    if (exact_inlier(wp.x, wp.y, cx, cy, dv.x, dv.y, exact_norm(dv.x, dv.y), fc.thr)) {  // :353
-      const float nx = __fmul_rn(dv.y, -1.0f);  // normal = (-dy, dx)                    :349
-      const float ny = dv.x;
-      const float bb = __fadd_rn(__fmul_rn(nx, cx), __fmul_rn(ny, cy));  // :359
-      s[0] += (double)__fmul_rn(nx, nx);  // :361 float32 products, float64 accumulation
-      s[1] += (double)__fmul_rn(nx, ny);
-      s[2] += (double)__fmul_rn(ny, ny);
-      s[3] += (double)__fmul_rn(nx, bb);  // :362
-      s[4] += (double)__fmul_rn(ny, bb);
+#pragma unroll
+  for (int k = 0; k < kRefineTile / 256; ++k) {
+    const int t = tile * kRefineTile + k * 256 + tid;
+    if (t < tn) {
+      const uint32_t pk = pix[t];
+      const int x = pk & 0xFFFFu, y = pk >> 16;
+      const float2 dv = load_dir(vimg, d.w, d.vn, x, y, v);
+      const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
+      const bool in = exact_inlier(wp.x, wp.y, cx, cy, dv.x, dv.y, exact_norm(dv.x, dv.y), fc.thr);  // :353
+      const bool finite = fabsf(dv.x) <= 3.0e38f && fabsf(dv.y) <= 3.0e38f;
+      if (in || !finite) {  // finite outliers contribute exact zeros
+        const float fl = in ? 1.0f : 0.0f;
+        const float nx = __fmul_rn(__fmul_rn(dv.y, -1.0f), fl);  // normal = (-dy, dx) * inlier      :349, :356
+        const float ny = __fmul_rn(dv.x, fl);
+        const float bb = __fadd_rn(__fmul_rn(nx, cx), __fmul_rn(ny, cy));  // :359
+        s[0] += (double)__fmul_rn(nx, nx);  // :361
+        s[1] += (double)__fmul_rn(nx, ny);
+        s[2] += (double)__fmul_rn(ny, ny);
+        s[3] += (double)__fmul_rn(nx, bb);  // :362
+        s[4] += (double)__fmul_rn(ny, bb);
+      }
     }
   }
   __shared__ double sred[8][5];
@@ -485,7 +538,7 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc, 
   if (tid < 5) {
     double t = 0;
     for (int k = 0; k < 8; ++k) t += sred[k][tid];
-    ws.sums[((size_t)job * d.vn + v) * 5 + tid] = t;
+    ws.partial[((size_t)rt * d.vn + v) * 5 + tid] = t;
   }
 }
 
@@ -502,56 +555,60 @@ __device__ __forceinline__ bool invertible_2x2(float af, float bf, float cf) {
     s0 = s1;
     s1 = t;
   }
-  if (s1 == 0.0) return false;  // inf or nan condition number
+  if (!(s1 > 0.0)) return false;  // zero or NaN smallest singular value: condition number inf / nan
   const double cnd = __ddiv_rn(s0, s1);
   return isfinite(cnd) && cnd < 1000000.0;  // :270-272, eps_inv = float32(1/1e-6)
 }
 
-// one thread per job
-__global__ void __launch_bounds__(128) k_solve(WS ws, Dims d, float* __restrict__ out, casa_ransac_debug dbg) {
-  const int job = blockIdx.x * 128 + threadIdx.x;
-  if (job >= d.J) return;
+// one warp per job, lane v handles keypoint v
+__global__ void __launch_bounds__(32) k_solve(WS ws, Dims d, float* __restrict__ out, casa_ransac_debug dbg) {
+  const int job = blockIdx.x, v = threadIdx.x;
   const int flags = ws.job_flags[job];
   const int tn = ws.job_tn[job];
-  float2* o = reinterpret_cast<float2*>(out) + (size_t)job * d.vn;
   const bool dead = (flags & JOB_GATED) || tn <= 0;
-  bool all_inv = !dead;
-  if (!dead) {
-    for (int v = 0; v < d.vn; ++v) {
-      const double* s = ws.sums + ((size_t)job * d.vn + v) * 5;
-      const float a = (float)s[0], b = (float)s[1], c = (float)s[2];
-      all_inv = all_inv && invertible_2x2(a, b, c);
-      if (dbg.ata) {
-        float* q = dbg.ata + ((size_t)job * d.vn + v) * 3;
-        q[0] = a; q[1] = b; q[2] = c;
-      }
-      if (dbg.atb) {
-        float* q = dbg.atb + ((size_t)job * d.vn + v) * 2;
-        q[0] = (float)s[3]; q[1] = (float)s[4];
-      }
-    }
+  float s[5] = {0, 0, 0, 0, 0};
+  bool inv = true;
+  if (!dead && v < d.vn) {
+    const int r0 = ws.rtile_start[job], r1 = ws.rtile_start[job + 1];
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int rt = r0; rt < r1; ++rt)  // tiles in order: bit-reproducible sums
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] += ws.partial[((size_t)rt * d.vn + v) * 5 + k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s[k] = (float)acc[k];  // ATA / ATb are float32 tensors in the reference
+    inv = invertible_2x2(s[0], s[1], s[2]);
   }
-  for (int v = 0; v < d.vn; ++v) {
+  const bool all_inv = !dead && __all_sync(0xffffffffu, inv);  // :364 — one singular keypoint un-refines all
+  if (v < d.vn) {
     float2 r = make_float2(0.f, 0.f);  // :291-292
     if (!dead) {
       r = ws.win_pts[job * d.vn + v];  // :364-365
       if (all_inv) {                   // :367  inv(ATA) @ ATb, closed form in float64 on the float32 sums
-        const double* s = ws.sums + ((size_t)job * d.vn + v) * 5;
-        const double a = (float)s[0], b = (float)s[1], c = (float)s[2], g0 = (float)s[3], g1 = (float)s[4];
+        const double a = s[0], b = s[1], c = s[2], g0 = s[3], g1 = s[4];
         const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, b));
         r.x = (float)__ddiv_rn(__dsub_rn(__dmul_rn(c, g0), __dmul_rn(b, g1)), det);
         r.y = (float)__ddiv_rn(__dsub_rn(__dmul_rn(a, g1), __dmul_rn(b, g0)), det);
       }
     }
-    o[v] = r;
+    reinterpret_cast<float2*>(out)[(size_t)job * d.vn + v] = r;
+    if (dbg.ata) {
+      float* q = dbg.ata + ((size_t)job * d.vn + v) * 3;
+      q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+    }
+    if (dbg.atb) {
+      float* q = dbg.atb + ((size_t)job * d.vn + v) * 2;
+      q[0] = s[3]; q[1] = s[4];
+    }
     if (dbg.win_pts) reinterpret_cast<float2*>(dbg.win_pts)[(size_t)job * d.vn + v] = dead ? make_float2(0.f, 0.f) : ws.win_pts[job * d.vn + v];
     if (dbg.win_ratio) dbg.win_ratio[(size_t)job * d.vn + v] = dead ? 0.f : ws.win_ratio[job * d.vn + v];
   }
-  if (dbg.refined) dbg.refined[job] = (!dead && all_inv) ? 1 : 0;
-  if (dbg.tn0) dbg.tn0[job] = ws.job_tn0[job];
-  if (dbg.tn) dbg.tn[job] = (flags & JOB_GATED) ? 0 : tn;
-  if (dbg.rounds) dbg.rounds[job] = dead ? 0 : ws.job_rounds[job];
-  if (dbg.pix_off) dbg.pix_off[job] = ws.job_off[job];
+  if (v == 0) {
+    if (dbg.refined) dbg.refined[job] = all_inv ? 1 : 0;
+    if (dbg.tn0) dbg.tn0[job] = ws.job_tn0[job];
+    if (dbg.tn) dbg.tn[job] = (flags & JOB_GATED) ? 0 : tn;
+    if (dbg.rounds) dbg.rounds[job] = dead ? 0 : ws.job_rounds[job];
+    if (dbg.pix_off) dbg.pix_off[job] = ws.job_off[job];
+  }
 }
 
 }  // namespace casa

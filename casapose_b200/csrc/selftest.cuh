@@ -111,17 +111,19 @@ __device__ __forceinline__ unsigned mix_loop(int iters, float a, float b) {
 }
 
 // The shipped k_score inner loop (chunk-local form): 4 FFMA + FADD + LEA.HI + 1/2 FMNMX3 per unit.
+// Exploration knobs: MINMODE 0 none, 1 FMNMX3 per pair (shipped), 2 FMNMX per unit;
+//                    CNTMODE 0 none, 1 LEA.HI (shipped), 2 IMAD.HI (FMA pipe), 3 alternate LEA.HI / IMAD.HI
+template <int MINMODE, int CNTMODE>
 __device__ __forceinline__ unsigned mix_shipped(int iters, float a, float b) {
-  float hx[8], hy[8], mn[4];
+  float hx[8], hy[8], mn[8];
   unsigned nlo[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     hx[i] = a * (float)(i + 1);
     hy[i] = b + (float)i;
     nlo[i] = 0u;
+    mn[i] = 3.0e38f;
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) mn[i] = 3.0e38f;
   float4 A = make_float4(0.6f, -0.8f, a, b);
   float2 B = make_float2(-0.08f, -0.11f);
   for (int it = 0; it < iters; ++it) {
@@ -135,9 +137,62 @@ __device__ __forceinline__ unsigned mix_shipped(int iters, float a, float b) {
         const float s1 = fmaf(B.x, hx[i + 1], fmaf(B.y, hy[i + 1], A.w));
         const float t0v = fabsf(p0) + s0;
         const float t1v = fabsf(p1) + s1;
-        nlo[i] += __float_as_uint(t0v) >> 31;
-        nlo[i + 1] += __float_as_uint(t1v) >> 31;
-        mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t0v)), fabsf(t1v));
+        if (CNTMODE == 1 || (CNTMODE == 3 && (i & 2))) {
+          nlo[i] += __float_as_uint(t0v) >> 31;
+          nlo[i + 1] += __float_as_uint(t1v) >> 31;
+        } else if (CNTMODE == 2 || CNTMODE == 3) {
+          nlo[i] = __umulhi(__float_as_uint(t0v), 2u) + nlo[i];
+          nlo[i + 1] = __umulhi(__float_as_uint(t1v), 2u) + nlo[i + 1];
+        } else {
+          nlo[i] ^= __float_as_uint(t0v + t1v);  // keep t alive with one op per pair
+        }
+        if (MINMODE == 1) {
+          mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t0v)), fabsf(t1v));
+        } else if (MINMODE == 2) {
+          mn[i] = fminf(mn[i], fabsf(t0v));
+          mn[i + 1] = fminf(mn[i + 1], fabsf(t1v));
+        }
+      }
+      A.z += 0.25f;
+      A.w -= 0.125f;
+    }
+  }
+  unsigned tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += nlo[i] + __float_as_uint(mn[i]);
+  return tot;
+}
+
+// Packed form of the shipped loop: the four FMAs of two hypotheses as FFMA2 (fma.rn.f32x2).
+// PIXU = pixels per iteration (unroll), ADD2 = 1 uses FADD2 for t (then |p| needs a separate abs)
+template <int PIXU>
+__device__ __forceinline__ unsigned mix_packed(int iters, float a, float b) {
+  float2 hx2[4], hy2[4];
+  float mn[4];
+  unsigned nlo[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hx2[i] = make_float2(a * (float)(2 * i + 1), a * (float)(2 * i + 2));
+    hy2[i] = make_float2(b + (float)(2 * i), b + (float)(2 * i + 1));
+    mn[i] = 3.0e38f;
+    nlo[2 * i] = nlo[2 * i + 1] = 0u;
+  }
+  float4 A = make_float4(0.6f, -0.8f, a, b);
+  float2 B = make_float2(-0.08f, -0.11f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int q = 0; q < PIXU; ++q) {
+      const float2 Ax2 = make_float2(A.x, A.x), Ay2 = make_float2(A.y, A.y), Az2 = make_float2(A.z, A.z);
+      const float2 Aw2 = make_float2(A.w, A.w), Bx2 = make_float2(B.x, B.x), By2 = make_float2(B.y, B.y);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 p2 = __ffma2_rn(Ax2, hy2[i], __ffma2_rn(Ay2, hx2[i], Az2));
+        const float2 s2 = __ffma2_rn(Bx2, hx2[i], __ffma2_rn(By2, hy2[i], Aw2));
+        const float t0v = fabsf(p2.x) + s2.x;
+        const float t1v = fabsf(p2.y) + s2.y;
+        nlo[2 * i] += __float_as_uint(t0v) >> 31;
+        nlo[2 * i + 1] += __float_as_uint(t1v) >> 31;
+        mn[i] = fminf(fminf(mn[i], fabsf(t0v)), fabsf(t1v));
       }
       A.z += 0.25f;
       A.w -= 0.125f;
@@ -196,7 +251,11 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float s
 #pragma unroll
     for (int k = 0; k < 16; ++k) r += acc[k];
   } else if (VARIANT == 3) {
-    r = __uint_as_float(mix_shipped(iters, a, b));
+    r = __uint_as_float(mix_shipped<1, 1>(iters, a, b));
+  } else if (VARIANT == 40) {
+    r = __uint_as_float(mix_packed<2>(iters, a, b));
+  } else if (VARIANT >= 20) {
+    r = __uint_as_float(mix_shipped<(VARIANT - 20) / 4, (VARIANT - 20) % 4>(iters, a, b));
   } else {
     r = __uint_as_float(mix_loop<(VARIANT - 10) / 3, (VARIANT - 10) % 3>(iters, a, b));
   }

@@ -132,6 +132,16 @@ int casa_last_status(casa_handle* h, uint32_t* status);
 int casa_last_launches(casa_handle* h, int64_t* launches);
 
 /*
+ * Measurement hooks (bench.py).  With timing enabled every scoring-kernel launch is bracketed by
+ * CUDA events on the caller's stream; casa_get_timing returns, for the LAST casa_ransac_vote call,
+ * the summed duration of its scoring launches (ms), their number, and the filter statistics
+ * stats[0] = units scored (hypothesis x pixel x keypoint tests), stats[1] = units decided by the
+ * exact predicate, stats[2] = exact-list hypotheses, stats[3] = stage-2 (hypothesis pair, chunk) events.
+ */
+int casa_set_timing(casa_handle* h, int enable);
+int casa_get_timing(casa_handle* h, double* score_ms, int64_t* score_launches, uint64_t* stats4);
+
+/*
  * Self-test of the filtered inlier predicate: draws n adversarial (pixel, hypothesis)
  * pairs concentrated on the decision boundary and compares filter+fallback with the
  * reference-exact float32 sequence (ransac_voting.py:230-249).

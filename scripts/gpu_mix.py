@@ -8,9 +8,12 @@ from casapose_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
 h = _lib.handle(0)
-names = {0: "FFMA", 1: "FFMA2", 2: "FFMA 3-reg", 3: "shipped loop"}
-for k in (1, 2, 3, 4, 5, 6, 8):
-    names[3 + 100 * k] = "shipped loop, %d blocks (%d warps)/SM" % (k, 8 * k)
+names = {0: "FFMA", 3: "shipped loop", 40: "packed FFMA2 loop"}
+mins = ["no min", "FMNMX3/pair", "FMNMX/unit"]
+cnts = ["no count", "LEA.HI", "IMAD.HI", "LEA/IMAD alternate"]
+for m in range(3):
+    for c in range(4):
+        names[20 + m * 4 + c] = "loop: %s, %s" % (mins[m], cnts[c])
 for v in sorted(names):
     tf, ms = C.c_double(), C.c_double()
     _lib.check(L.casa_measure_fp32_peak(h, v, C.byref(tf), C.byref(ms)))

@@ -22,6 +22,7 @@ STATUS_BITS = {
     2: "PIX_OVERFLOW",
     4: "IDX_RANGE",
     8: "EMPTY_AFTER_CAP",
+    16: "LS_NONFINITE",
 }
 
 
@@ -49,8 +50,12 @@ class LsParams(C.Structure):
     _fields_ = [
         ("b", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("num_classes", C.c_int32), ("vn", C.c_int32),
         ("sigmoid_weights", C.c_int32), ("filter_estimates", C.c_int32), ("second_largest", C.c_int32),
-        ("min_component", C.c_int32), ("reserved", C.c_int32),
+        ("min_component", C.c_int32), ("check_finite", C.c_int32),
     ]
+
+
+class LsDebug(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("sums", "labels", "selected", "parent", "tn")]
 
 
 EXPORTS = {
@@ -63,6 +68,8 @@ EXPORTS = {
     "casa_ransac_vote": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(RansacDebug), C.c_void_p]),
     "casa_ransac_vote_host": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "casa_ls_vote": (C.c_int, [C.c_void_p, C.POINTER(LsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.POINTER(LsDebug), C.c_void_p]),
     "casa_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "casa_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "casa_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

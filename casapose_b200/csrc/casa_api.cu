@@ -341,6 +341,87 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   return CASA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ LS layer
+
+extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct,
+                            const float* conf, float* out_points, const casa_ls_debug* debug, void* stream) {
+  if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
+  if (!seg || !direct || !conf || !out_points) return fail(CASA_ERR_INVALID, "seg / direct / conf / out_points must not be NULL");
+  if (p->num_classes < 2 || p->num_classes > 33) return fail(CASA_ERR_INVALID, "num_classes=%d outside 2..33", p->num_classes);
+  casa_ransac_params rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.b = p->b; rp.h = p->h; rp.w = p->w; rp.oc = p->num_classes - 1; rp.vn = p->vn;
+  rp.round_hyp_num = 1; rp.max_iter = 1;
+  rp.min_num = 0.f; rp.max_num = 3.0e38f; rp.inlier_thresh = 0.99f; rp.confidence = 0.99f;
+  Layout L;
+  int rc = make_layout(&rp, h->score_p, L);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const Dims& d = L.d;
+  const size_t npx = (size_t)d.b * d.hw;
+  size_t cur = L.total;
+  const size_t off_cls9 = bump(cur, npx), off_parent = bump(cur, npx * 4), off_count = bump(cur, npx * 4),
+               off_roots = bump(cur, npx * 4), off_nroots = bump(cur, (size_t)d.b * 4), off_sel = bump(cur, (size_t)d.J * 4);
+  rc = ensure(&h->ws_mem, &h->ws_bytes, cur);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  WS ws = make_ws(L, h->ws_mem, true);
+  char* base = (char*)h->ws_mem;
+  LsWS lw;
+  lw.cls9 = (unsigned char*)(base + off_cls9);
+  lw.parent = (int*)(base + off_parent);
+  lw.count = (int*)(base + off_count);
+  lw.roots = (int*)(base + off_roots);
+  lw.nroots = (int*)(base + off_nroots);
+  lw.sel = (int*)(base + off_sel);
+  LsDims ld;
+  ld.b = d.b; ld.h = d.h; ld.w = d.w; ld.nc = p->num_classes; ld.oc = d.oc; ld.vn = d.vn; ld.hw = d.hw;
+  ld.sigmoid_weights = p->sigmoid_weights ? 1 : 0;
+  ld.filter = p->filter_estimates ? 1 : 0;
+  ld.bins = p->second_largest ? 3 : 2;
+  ld.which = p->second_largest ? 2 : 1;
+  ld.min_component = p->min_component > 0 ? p->min_component : 50;
+  casa_ls_debug dbg;
+  memset(&dbg, 0, sizeof(dbg));
+  if (debug) dbg = *debug;
+  int64_t launches = 0;
+
+  CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
+  k_ls_classify<<<dim3(d.nct, d.b), 256, 0, st>>>(seg, ws, d, lw, ld);
+  k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
+  k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
+  k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
+  k_init_jobs<<<(d.J + 255) / 256, 256, 0, st>>>(ws, d);
+  k_plan<<<1, 1024, 0, st>>>(ws, d, 0);
+  launches += 6;
+  if (ld.filter) {
+    k_cc_init<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(lw, ld);
+    k_cc_merge<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
+    k_cc_flatten<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
+    k_cc_select<<<d.J, 256, 0, st>>>(lw, ld);
+    launches += 4;
+  }
+  const int grid_x = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
+  k_ls_reduce<<<dim3(grid_x, d.vn), 256, 0, st>>>(ws, d, lw, ld, seg, direct, conf);
+  k_ls_solve<<<d.J, 32, 0, st>>>(ws, d, ld, out_points, dbg.sums);
+  launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  if (dbg.labels) CUDA_TRY(cudaMemcpyAsync(dbg.labels, lw.cls9, npx, cudaMemcpyDeviceToDevice, st));
+  if (dbg.parent && ld.filter) CUDA_TRY(cudaMemcpyAsync(dbg.parent, lw.parent, npx * 4, cudaMemcpyDeviceToDevice, st));
+  if (dbg.selected && ld.filter) CUDA_TRY(cudaMemcpyAsync(dbg.selected, lw.sel, (size_t)d.J * 4, cudaMemcpyDeviceToDevice, st));
+  if (dbg.tn) CUDA_TRY(cudaMemcpyAsync(dbg.tn, ws.job_tn, (size_t)d.J * 4, cudaMemcpyDeviceToDevice, st));
+  h->last_launches = launches;
+  if (p->check_finite) {
+    CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->last_status = (uint32_t)h->pinned[CTRL_STATUS];
+    if (h->last_status & CASA_STATUS_LS_NONFINITE)
+      return fail(CASA_ERR_INPUT, "CoordLSVotingWeighted: non-finite R / q / p (the reference asserts here, voting_layers_2d.py:109-121)");
+  }
+  return CASA_OK;
+}
+
 extern "C" int casa_last_status(casa_handle* h, uint32_t* status) {
   if (!h || !status) return fail(CASA_ERR_INVALID, "NULL argument");
   *status = h->last_status;

@@ -1,4 +1,355 @@
-// K5 — dense weighted least-squares voting of CoordLSVotingWeighted.calc (implemented below).
+// K5/K6 — CoordLSVotingWeighted (/root/reference/casapose/pose_estimation/voting_layers_2d.py:5-122).
+//
+//   k_ls_classify  hot_seg = softmax(1e6 * seg)[..., 1:] (:38-41) per pixel; writes the class-membership
+//                  word (hot != 0) for the shared compaction kernels (compaction.cuh) and, for the
+//                  component filter, the class whose hot value truncates to 1 (int(hot + 0.1), :44);
+//   k_cc_*         4-connected components of all classes at once (union-find on the label map; stands in
+//                  for tfa.image.connected_components :53), component sizes, and the reference's selection
+//                  bincount -> (<50 -> 0) -> top_k -> index[1] or [2]  (:64-76) including its quirks
+//                  (label 0 = background competes; zero counts tie-break towards the lowest label);
+//   k_ls_reduce    per (class, keypoint, 1024-pixel tile): n = dir/|dir|, R = w (I - n n^T), q = R p with
+//                  p = ((y+.5)/H, (x+.5)/H), weighted by hot (and the component mask); float32 elementwise
+//                  exactly as the reference forms them, float64 accumulation (:113-114), fixed order;
+//   k_ls_solve     ordered sum of the tiles, 2x2 pseudo-inverse in float64 (:116-120), * height (:122).
+// HBM-bound: algorithmic bytes per frame h*w*4*((1+oc) + 2*vn + vn); only masked pixels of the direction
+// and confidence fields are actually read (gathered through the pixel lists).
 #pragma once
 #include "common.cuh"
-namespace casa {}
+
+namespace casa {
+
+constexpr unsigned LS_STATUS_NONFINITE = 16u;  // a non-finite R / q / p (the reference's tf.Assert :109-121)
+
+struct LsDims {
+  int b, h, w, nc, oc, vn, hw;
+  int sigmoid_weights, filter, which, bins, min_component;
+};
+
+struct LsWS {
+  unsigned char* cls9;  // [b*hw]  class (1..oc) with int(hot + 0.1) == 1, else 0
+  int* parent;          // [b*hw]  union-find forest over same-class 4-neighbours (index inside the image)
+  int* count;           // [b*hw]  component size at the root pixel
+  int* roots;           // [b*hw]  list of root pixels per image
+  int* nroots;          // [b]
+  int* sel;             // [J]     selected component: root pixel, -1 = none, -2 = label 0 (background)
+};
+
+// softmax(seg * 1e6) in float32 (:38-41): z = x * 1e6; e = exp(z - max z); e / sum e
+__device__ __forceinline__ void hard_softmax(const float* __restrict__ row, int nc, float* hot) {
+  float m = -3.4e38f;
+  for (int c = 0; c < nc; ++c) {
+    hot[c] = __fmul_rn(__ldg(row + c), 1.0e6f);
+    m = fmaxf(m, hot[c]);
+  }
+  float s = 0.f;
+  for (int c = 0; c < nc; ++c) {
+    hot[c] = expf(__fsub_rn(hot[c], m));
+    s = __fadd_rn(s, hot[c]);
+  }
+  for (int c = 0; c < nc; ++c) hot[c] = __fdiv_rn(hot[c], s);
+}
+
+__device__ __forceinline__ float hard_softmax_one(const float* __restrict__ row, int nc, int cls) {
+  float m = -3.4e38f;
+  for (int c = 0; c < nc; ++c) m = fmaxf(m, __fmul_rn(__ldg(row + c), 1.0e6f));
+  float s = 0.f, e = 0.f;
+  for (int c = 0; c < nc; ++c) {
+    const float t = expf(__fsub_rn(__fmul_rn(__ldg(row + c), 1.0e6f), m));
+    s = __fadd_rn(s, t);
+    if (c == cls) e = t;
+  }
+  return __fdiv_rn(e, s);
+}
+
+// same tiling and outputs as k_mask_bits (compaction.cuh), fed by the segmentation logits
+__global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ seg, WS ws, Dims d, LsWS lw, LsDims ld) {
+  const int img = blockIdx.y, tile = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int scnt[32];
+  if (tid < 32) scnt[tid] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = tile * kCountTile + k * 256 + tid;
+    uint32_t m = 0;
+    if (p < d.hw) {
+      float hot[33];
+      hard_softmax(seg + ((size_t)img * d.hw + p) * ld.nc, ld.nc, hot);
+      int c9 = 0;
+      for (int c = 1; c < ld.nc; ++c) {
+        m |= (uint32_t)(hot[c] != 0.f) << (c - 1);
+        if ((int)__fadd_rn(hot[c], 0.1f) == 1) c9 = c;  // :44 (at most one class can reach 0.9)
+      }
+      ws.bits[(size_t)img * d.hw + p] = m;
+      lw.cls9[(size_t)img * d.hw + p] = (unsigned char)c9;
+    }
+    for (int c = 0; c < d.oc; ++c) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
+      if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+    }
+  }
+  __syncthreads();
+  if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
+}
+
+// ---------------------------------------------------------------------------------- connected components
+__device__ __forceinline__ int uf_find(const int* parent, int x) {
+  int p = parent[x];
+  while (p != x) {
+    x = p;
+    p = parent[x];
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(&parent[a], b);  // hang the larger root under the smaller one
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cc_init(LsWS lw, LsDims ld) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (size_t)ld.b * ld.hw) return;
+  lw.parent[i] = (int)(i % ld.hw);
+  lw.count[i] = 0;
+  if (i < (size_t)ld.b) lw.nroots[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_cc_merge(LsWS lw, LsDims ld) {
+  const int img = blockIdx.y;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= ld.hw) return;
+  const unsigned char* cls = lw.cls9 + (size_t)img * ld.hw;
+  int* parent = lw.parent + (size_t)img * ld.hw;
+  const int c = cls[p];
+  if (c == 0) return;
+  const int y = p / ld.w, x = p - y * ld.w;
+  if (x > 0 && cls[p - 1] == c) uf_union(parent, p, p - 1);
+  if (y > 0 && cls[p - ld.w] == c) uf_union(parent, p, p - ld.w);
+}
+
+__global__ void __launch_bounds__(256) k_cc_flatten(LsWS lw, LsDims ld) {
+  const int img = blockIdx.y;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= ld.hw) return;
+  if (lw.cls9[(size_t)img * ld.hw + p] == 0) return;
+  int* parent = lw.parent + (size_t)img * ld.hw;
+  const int r = uf_find(parent, p);
+  parent[p] = r;
+  atomicAdd(&lw.count[(size_t)img * ld.hw + r], 1);
+  if (r == p) lw.roots[(size_t)img * ld.hw + atomicAdd(&lw.nroots[img], 1)] = p;
+}
+
+// one block per (image, class): bincount -> threshold -> top_k -> pick index `which` (:64-76).
+// Entries are label 0 (every pixel outside the class's int mask) and the components; the component with
+// the smaller root pixel has the smaller tfa label.  key = (value << 32) | ~label : descending order.
+__global__ void __launch_bounds__(256) k_cc_select(LsWS lw, LsDims ld) {
+  const int job = blockIdx.x, img = job / ld.oc, c = job - img * ld.oc;
+  const int tid = threadIdx.x;
+  const int n = lw.nroots[img];
+  const int* roots = lw.roots + (size_t)img * ld.hw;
+  unsigned long long top[3] = {0ull, 0ull, 0ull};
+  int npix = 0, ncomp = 0;
+  for (int i = tid; i < n; i += 256) {
+    const int r = roots[i];
+    if (lw.cls9[(size_t)img * ld.hw + r] != c + 1) continue;
+    const int cnt = lw.count[(size_t)img * ld.hw + r];
+    npix += cnt;
+    ++ncomp;
+    const unsigned v = cnt < ld.min_component ? 0u : (unsigned)cnt;  // :66
+    unsigned long long key = ((unsigned long long)v << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)(r + 1));
+    for (int k = 0; k < 3; ++k)
+      if (key > top[k]) {
+        const unsigned long long t = top[k];
+        top[k] = key;
+        key = t;
+      }
+  }
+  __shared__ unsigned long long stop[256 * 3];
+  __shared__ int snp[256], snc[256];
+  for (int k = 0; k < 3; ++k) stop[tid * 3 + k] = top[k];
+  snp[tid] = npix;
+  snc[tid] = ncomp;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long best[3] = {0ull, 0ull, 0ull};
+    int tp = 0, tc = 0;
+    for (int i = 0; i < 256; ++i) {
+      tp += snp[i];
+      tc += snc[i];
+      for (int k = 0; k < 3; ++k) {
+        unsigned long long key = stop[i * 3 + k];
+        if (key == 0ull) continue;
+        for (int j = 0; j < 3; ++j)
+          if (key > best[j]) {
+            const unsigned long long t = best[j];
+            best[j] = key;
+            key = t;
+          }
+      }
+    }
+    const int bg = ld.hw - tp;  // label 0 of this class's int image
+    const unsigned vbg = bg < ld.min_component ? 0u : (unsigned)bg;
+    unsigned long long key = ((unsigned long long)vbg << 32) | 0xFFFFFFFFull;  // label 0: wins every tie
+    for (int j = 0; j < 3; ++j)
+      if (key > best[j]) {
+        const unsigned long long t = best[j];
+        best[j] = key;
+        key = t;
+      }
+    int sel = -1;                       // padding label: matches no pixel
+    if (ld.which < tc + 1) {            // real entries: label 0 and tc components
+      const unsigned long long k = best[ld.which];
+      const unsigned lab = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+      sel = lab == 0u ? -2 : (int)lab - 1;
+    }
+    lw.sel[job] = sel;
+  }
+}
+
+// ---------------------------------------------------------------------------------- weighted reduction
+__device__ __forceinline__ float ls_weight(float x, int sigmoid_weights) {
+  if (sigmoid_weights) return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));  // :33 (sigmoid_scale = 1)
+  const float thr = 13.942385f;  // -(log(eps_f32) + 2), Eigen's softplus functor (:35)
+  const float ex = expf(x);
+  return x > thr ? x : (x < -thr ? ex : logf(__fadd_rn(ex, 1.0f)));
+}
+
+// persistent over the refinement tiles: blockIdx.x strides over tiles, blockIdx.y = keypoint
+__global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDims ld, const float* __restrict__ seg,
+                                                   const float* __restrict__ direct, const float* __restrict__ conf) {
+  const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_rtiles = ws.rtile_start[d.J];
+  __shared__ double sred[8][5];
+  const float fh = (float)ld.h;
+  for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
+    int lo = 0, hi = d.J;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ws.rtile_start[mid] <= rt) lo = mid; else hi = mid;
+    }
+    const int job = lo, tile = rt - ws.rtile_start[job];
+    const int tn = ws.job_tn[job];
+    const int img = job / d.oc, c = job - img * d.oc;
+    const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
+    const int sel = ld.filter ? lw.sel[job] : 0;
+    double s[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < kRefineTile / 256; ++k) {
+      const int t = tile * kRefineTile + k * 256 + tid;
+      if (t >= tn) continue;
+      const uint32_t pk = pix[t];
+      const int x = pk & 0xFFFFu, y = pk >> 16;
+      const size_t p = (size_t)img * ld.hw + (size_t)y * ld.w + x;
+      float wt = hard_softmax_one(seg + p * ld.nc, ld.nc, c + 1);  // hot_seg (:39-41)
+      if (ld.filter) {  // copy_components * hot_seg (:72-79)
+        const int c9 = lw.cls9[p];
+        const bool keep = sel == -2 ? (c9 != c + 1) : (sel >= 0 && c9 == c + 1 && lw.parent[p] == sel);
+        wt = __fmul_rn(keep ? 1.0f : 0.0f, wt);
+      }
+      if (wt == 0.f) continue;  // multiply_no_nan (:107-108)
+      const float2 dv = __ldg(reinterpret_cast<const float2*>(direct + (p * ld.vn + v) * 2));  // (n0, n1) = (dy, dx)
+      const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dv.x, dv.x), __fmul_rn(dv.y, dv.y)));  // :89
+      const float n0 = nrm != 0.f ? __fdiv_rn(dv.x, nrm) : 0.f;  // divide_no_nan :90
+      const float n1 = nrm != 0.f ? __fdiv_rn(dv.y, nrm) : 0.f;
+      const float wc = ls_weight(__ldg(conf + p * ld.vn + v), ld.sigmoid_weights);
+      const float r00 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n0, n0)), wc);  // :92-94
+      const float r01 = __fmul_rn(__fsub_rn(0.0f, __fmul_rn(n0, n1)), wc);
+      const float r11 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n1, n1)), wc);
+      const float cy = __fdiv_rn(__fadd_rn((float)y, 0.5f), fh);  // :97  (both axes over the height)
+      const float cx = __fdiv_rn(__fadd_rn((float)x, 0.5f), fh);  // :96
+      const float q0 = __fadd_rn(__fmul_rn(r00, cy), __fmul_rn(r01, cx));  // :103-105
+      const float q1 = __fadd_rn(__fmul_rn(r01, cy), __fmul_rn(r11, cx));
+      s[0] += (double)__fmul_rn(r00, wt);  // :108, :113
+      s[1] += (double)__fmul_rn(r01, wt);
+      s[2] += (double)__fmul_rn(r11, wt);
+      s[3] += (double)__fmul_rn(q0, wt);   // :107, :114
+      s[4] += (double)__fmul_rn(q1, wt);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+      if (lane == 0) sred[warp][k] = s[k];
+    }
+    __syncthreads();
+    if (tid < 5) {
+      double t = 0;
+      for (int k = 0; k < 8; ++k) t += sred[k][tid];
+      ws.partial[((size_t)rt * d.vn + v) * 5 + tid] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// Moore-Penrose inverse of the symmetric [[a,b],[b,c]] applied to (g0,g1); singular values below
+// rcond * max are dropped (tf.linalg.pinv default rcond = 10 * 2 * eps_f64, :116)
+__device__ __forceinline__ void pinv2x2_apply(double a, double b, double c, double g0, double g1, double& p0, double& p1) {
+  const double m = 0.5 * (a + c), dd = 0.5 * (a - c);
+  const double r = sqrt(dd * dd + b * b);
+  const double l1 = m + r, l2 = m - r;  // eigenvalues, l1 >= l2
+  const double smax = fmax(fabs(l1), fabs(l2));
+  const double cut = 4.440892098500626e-15 * smax;
+  p0 = p1 = 0.0;
+  if (!(smax > 0.0)) {
+    if (smax != smax) p0 = p1 = smax;  // NaN in, NaN out
+    return;
+  }
+  if (fabs(l1) > cut && fabs(l2) > cut) {
+    const double det = a * c - b * b;
+    p0 = (c * g0 - b * g1) / det;
+    p1 = (a * g1 - b * g0) / det;
+    return;
+  }
+  // rank one: project on the eigenvector of the dominant eigenvalue
+  const double l = fabs(l1) >= fabs(l2) ? l1 : l2;
+  double vx = b, vy = l - a;
+  if (fabs(l - c) > fabs(vy)) {
+    vx = l - c;
+    vy = b;
+  }
+  const double nn = vx * vx + vy * vy;
+  if (!(nn > 0.0)) {  // diagonal matrix with one zero entry
+    if (fabs(a) >= fabs(c)) p0 = g0 / a; else p1 = g1 / c;
+    return;
+  }
+  const double proj = (vx * g0 + vy * g1) / (nn * l);
+  p0 = vx * proj;
+  p1 = vy * proj;
+}
+
+// one warp per job, lane v = keypoint
+__global__ void __launch_bounds__(32) k_ls_solve(WS ws, Dims d, LsDims ld, float* __restrict__ out, double* dbg_sums) {
+  const int job = blockIdx.x, v = threadIdx.x;
+  if (v >= d.vn) return;
+  const int r0 = ws.rtile_start[job], r1 = ws.rtile_start[job + 1];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int rt = r0; rt < r1; ++rt)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] += ws.partial[((size_t)rt * d.vn + v) * 5 + k];
+  double p0, p1;
+  pinv2x2_apply(acc[0], acc[1], acc[2], acc[3], acc[4], p0, p1);
+  const float o0 = __fmul_rn((float)p0, (float)ld.h), o1 = __fmul_rn((float)p1, (float)ld.h);  // :122
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) bad |= !(fabs(acc[k]) <= 1.7e308);
+  bad |= !(fabsf(o0) <= 3.4e38f) || !(fabsf(o1) <= 3.4e38f);
+  if (bad) atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), LS_STATUS_NONFINITE);
+  reinterpret_cast<float2*>(out)[(size_t)job * d.vn + v] = make_float2(o0, o1);  // (y, x) pixels
+  if (dbg_sums)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dbg_sums[((size_t)job * d.vn + v) * 5 + k] = acc[k];
+}
+
+}  // namespace casa

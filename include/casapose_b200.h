@@ -43,6 +43,7 @@ typedef enum casa_status {
 #define CASA_STATUS_PIX_OVERFLOW 2u     /* sum_c tn0 > pix_capacity for some image            */
 #define CASA_STATUS_IDX_RANGE 4u        /* a caller-supplied idx was outside [0, tn)          */
 #define CASA_STATUS_EMPTY_AFTER_CAP 8u  /* the max_num down-sampling removed every pixel      */
+#define CASA_STATUS_LS_NONFINITE 16u    /* CoordLSVotingWeighted produced a non-finite R/q/p  */
 
 typedef struct casa_handle casa_handle;
 
@@ -125,6 +126,39 @@ int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, const float* m
  */
 int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
                           const float* vertex_host, float* out_points_host);
+
+/*
+ * CoordLSVotingWeighted(name, num_classes, num_points, sigmoid_weights, filter_estimates,
+ * output_second_largest_component)([seg, direct, w])
+ * (/root/reference/casapose/pose_estimation/voting_layers_2d.py:5-122).
+ *   seg     device float32 [b,h,w,num_classes]   segmentation logits (class 0 = background)
+ *   direct  device float32 [b,h,w,2*vn]          (dy,dx) per keypoint
+ *   conf    device float32 [b,h,w,vn]            confidence logits
+ *   out     device float32 [b,num_classes-1,vn,2]  (y,x) pixels            voting_layers_2d.py:122
+ * Fully asynchronous on `stream` unless check_finite is set (one 32-byte read-back that stands in
+ * for the reference's tf.Assert on non-finite R / q / p, :109-121 -> CASA_ERR_INPUT).
+ */
+typedef struct casa_ls_params {
+  int32_t b, h, w;
+  int32_t num_classes;       /* 1 + object classes, 2..33                                   */
+  int32_t vn;                /* num_points, 1..16                                           */
+  int32_t sigmoid_weights;   /* 0: softplus (:35), 1: sigmoid (:33)                         */
+  int32_t filter_estimates;  /* keep only the selected connected component (:43-79)         */
+  int32_t second_largest;    /* output_second_largest_component (:58-73)                    */
+  int32_t min_component;     /* 0 = the reference's 50 (:66)                                */
+  int32_t check_finite;
+} casa_ls_params;
+
+typedef struct casa_ls_debug {
+  double* sums;       /* [b,oc,vn,5]  float64 sums R00, R01, R11, q0, q1               :113-114 */
+  uint8_t* labels;    /* [b,h,w]      class whose int(hot + 0.1) is 1, else 0          :44      */
+  int32_t* selected;  /* [b,oc]       root pixel of the kept component, -1 none, -2 label 0 :72-76 */
+  int32_t* parent;    /* [b,h,w]      component root of every labelled pixel            :53      */
+  int32_t* tn;        /* [b,oc]       pixels with hot != 0                                       */
+} casa_ls_debug;
+
+int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct,
+                 const float* conf, float* out_points, const casa_ls_debug* debug, void* stream);
 
 /* Device status word of the last casa_ransac_vote on this handle (CASA_STATUS_* bits). */
 int casa_last_status(casa_handle* h, uint32_t* status);

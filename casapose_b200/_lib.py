@@ -36,7 +36,7 @@ class RansacParams(C.Structure):
         ("round_hyp_num", C.c_int32), ("max_iter", C.c_int32),
         ("inlier_thresh", C.c_float), ("confidence", C.c_float), ("min_num", C.c_float), ("max_num", C.c_float),
         ("seed", C.c_uint64), ("image_offset", C.c_int32), ("pix_capacity", C.c_int32),
-        ("force_exact", C.c_int32), ("reserved", C.c_int32),
+        ("force_exact", C.c_int32), ("vertex_per_class", C.c_int32),
     ]
 
 
@@ -67,6 +67,8 @@ EXPORTS = {
     "casa_ransac_workspace_bytes": (C.c_size_t, [C.POINTER(RansacParams)]),
     "casa_ransac_vote": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(RansacDebug), C.c_void_p]),
+    "casa_ransac_vote_seg": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(RansacDebug), C.c_void_p]),
     "casa_ransac_vote_host": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "casa_ls_vote": (C.c_int, [C.c_void_p, C.POINTER(LsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.POINTER(LsDebug), C.c_void_p]),

@@ -138,6 +138,7 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   d.seed_hi = (uint32_t)(p->seed >> 32);
   d.min_num = p->min_num; d.max_num = p->max_num; d.confidence = p->confidence;
   d.force_exact = p->force_exact;
+  d.vpc = p->vertex_per_class ? d.oc : 1;
   size_t cur = 0;
   const size_t J = d.J, jv = J * d.vn, jvh = jv * d.hn;
   L.off_bits = bump(cur, (size_t)d.b * d.hw * 4);
@@ -227,9 +228,9 @@ extern "C" size_t casa_ransac_workspace_bytes(const casa_ransac_params* p) {
 
 // ------------------------------------------------------------------------------------------------ ransac vote
 
-extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, const float* mask, const float* vertex,
-                                const int32_t* idxs, const float* selection, float* out_points,
-                                const casa_ransac_debug* debug, void* stream) {
+static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const float* mask, int mask_is_seg,
+                            const float* vertex, const int32_t* idxs, const float* selection, float* out_points,
+                            const casa_ransac_debug* debug, void* stream) {
   if (!h) return fail(CASA_ERR_INVALID, "handle is NULL");
   if (!mask || !vertex || !out_points) return fail(CASA_ERR_INVALID, "mask / vertex / out_points must not be NULL");
   Layout L;
@@ -253,7 +254,10 @@ extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, con
   h->score_launches = 0;
 
   const int vec4 = ((d.oc & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
-  k_mask_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d, vec4);
+  if (mask_is_seg)
+    k_seg_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d);
+  else
+    k_mask_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d, vec4);
   k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
   k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
   k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
@@ -314,6 +318,18 @@ extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, con
   return CASA_OK;
 }
 
+extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, const float* mask, const float* vertex,
+                                const int32_t* idxs, const float* selection, float* out_points,
+                                const casa_ransac_debug* debug, void* stream) {
+  return ransac_vote_impl(h, p, mask, 0, vertex, idxs, selection, out_points, debug, stream);
+}
+
+extern "C" int casa_ransac_vote_seg(casa_handle* h, const casa_ransac_params* p, const float* seg, const float* vertex,
+                                    const int32_t* idxs, const float* selection, float* out_points,
+                                    const casa_ransac_debug* debug, void* stream) {
+  return ransac_vote_impl(h, p, seg, 1, vertex, idxs, selection, out_points, debug, stream);
+}
+
 extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
                                      const float* vertex_host, float* out_points_host) {
   if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
@@ -324,7 +340,8 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t hw = (size_t)p->h * p->w;
   const size_t mask_b = ((size_t)p->b * hw * p->oc * 4 + 255) & ~size_t(255);
-  const size_t vert_b = ((size_t)p->b * hw * p->vn * 2 * 4 + 255) & ~size_t(255);
+  const size_t vfields = p->vertex_per_class ? (size_t)p->oc : 1;
+  const size_t vert_b = ((size_t)p->b * hw * vfields * p->vn * 2 * 4 + 255) & ~size_t(255);
   const size_t out_b = (size_t)p->b * p->oc * p->vn * 2 * 4;
   rc = ensure(&h->io_mem, &h->io_bytes, mask_b + vert_b + out_b);
   if (rc) return rc;
@@ -333,7 +350,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   float* dout = (float*)((char*)h->io_mem + mask_b + vert_b);
   cudaStream_t st = h->own_stream;
   CUDA_TRY(cudaMemcpyAsync(dmask, mask_host, (size_t)p->b * hw * p->oc * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(dvert, vertex_host, (size_t)p->b * hw * p->vn * 2 * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dvert, vertex_host, (size_t)p->b * hw * vfields * p->vn * 2 * 4, cudaMemcpyHostToDevice, st));
   rc = casa_ransac_vote(h, p, dmask, dvert, nullptr, nullptr, dout, nullptr, (void*)st);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));

@@ -76,6 +76,7 @@ struct Dims {
   uint32_t seed_lo, seed_hi;
   float min_num, max_num, confidence;
   int force_exact;
+  int vpc;  // vertex fields per pixel: 1, or oc when every class has its own field
 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {

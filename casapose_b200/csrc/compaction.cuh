@@ -61,6 +61,42 @@ __global__ void __launch_bounds__(256) k_mask_bits(const float* __restrict__ mas
   if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
 }
 
+// Fused pre-step (pose_evaluation.py:36-47): bit c of a pixel is set iff argmax(seg) == c + 1
+// (tf.argmax takes the first maximum; NaN scores never win, like Eigen's comparison-based arg-max).
+__global__ void __launch_bounds__(256) k_seg_bits(const float* __restrict__ seg, WS ws, Dims d) {
+  const int img = blockIdx.y, tile = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nc = d.oc + 1;
+  __shared__ int scnt[32];
+  if (tid < 32) scnt[tid] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = tile * kCountTile + k * 256 + tid;
+    uint32_t m = 0;
+    if (p < d.hw) {
+      const float* row = seg + ((size_t)img * d.hw + p) * nc;
+      float best = __ldg(row);
+      int arg = 0;
+      for (int c = 1; c < nc; ++c) {
+        const float v = __ldg(row + c);
+        if (v > best) {
+          best = v;
+          arg = c;
+        }
+      }
+      if (arg > 0) m = 1u << (arg - 1);
+      ws.bits[(size_t)img * d.hw + p] = m;
+    }
+    for (int c = 0; c < d.oc; ++c) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
+      if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+    }
+  }
+  __syncthreads();
+  if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
+}
+
 // one block (128 threads) per job: exclusive prefix of the job's tile counts, foreground_num (:287)
 __global__ void __launch_bounds__(128) k_scan_tiles(WS ws, Dims d) {
   const int job = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

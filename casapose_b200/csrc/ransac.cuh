@@ -16,8 +16,10 @@
 
 namespace casa {
 
+// vertex[img, y, x, (field,) v, 0:2] = (dy, dx)  ->  (dx, dy) like tf.reverse(..., axis=[2]) at :308.
+// `vn` here is the number of keypoint slots per pixel row (vn * fields) and `v` the slot (field * vn + v):
+// callers fold the per-class field of PVNet-style outputs (pose_evaluation.py:38-45) into both.
 __device__ __forceinline__ float2 load_dir(const float* __restrict__ vimg, int w, int vn, int x, int y, int v) {
-  // vertex[img, y, x, v, 0:2] = (dy, dx)  ->  (dx, dy) like tf.reverse(..., axis=[2]) at :308
   const float2 t = __ldg(reinterpret_cast<const float2*>(vimg + ((size_t)(y * w + x) * vn + v) * 2));
   return make_float2(t.y, t.x);
 }
@@ -48,8 +50,9 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
   const int tn = ws.job_tn[job];
   const int img = job / d.oc, cls = job - img * d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
-  const float* vimg = vertex + (size_t)img * d.hw * d.vn * 2;
   const int h = e / d.vn, v = e - h * d.vn;
+  const int vslots = d.vn * d.vpc, vs = (d.vpc > 1 ? cls * d.vn : 0) + v;
+  const float* vimg = vertex + (size_t)img * d.hw * vslots * 2;
   int2 ip;
   if (idxs) {
     const int32_t* src = idxs + ((((size_t)job * d.max_iter + rnd) * d.hn + h) * d.vn + v) * 2;
@@ -67,8 +70,8 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
   const int x0 = p0 & 0xFFFFu, y0 = p0 >> 16, x1 = p1 & 0xFFFFu, y1 = p1 >> 16;
   const float2 c0 = make_float2((float)x0 + 0.5f, (float)y0 + 0.5f);  // :306
   const float2 c1 = make_float2((float)x1 + 0.5f, (float)y1 + 0.5f);
-  const float2 d0 = load_dir(vimg, d.w, d.vn, x0, y0, v);
-  const float2 d1 = load_dir(vimg, d.w, d.vn, x1, y1, v);
+  const float2 d0 = load_dir(vimg, d.w, vslots, x0, y0, vs);
+  const float2 d1 = load_dir(vimg, d.w, vslots, x1, y1, vs);
   const float2 hp = exact_hypothesis(c0, c1, d0, d1);
   const size_t o = ((size_t)job * d.vn + v) * d.hn + h;
   ws.hyp_true[o] = hp;
@@ -263,7 +266,8 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     const int img = job / a.d.oc;
     const int tn = a.ws.job_tn[job];
     const uint32_t* pix = a.ws.pix + (size_t)img * a.d.cap + a.ws.job_off[job];
-    const float* vimg = a.vertex + (size_t)img * a.d.hw * a.d.vn * 2;
+    const int vslots = a.d.vn * a.d.vpc, vs = (a.d.vpc > 1 ? (job - img * a.d.oc) * a.d.vn : 0) + v;
+    const float* vimg = a.vertex + (size_t)img * a.d.hw * vslots * 2;
     const int t0 = chunk * kChunk;
     const int npx = min(kChunk, tn - t0);
 
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
         const uint32_t pk = pix[t0 + q];
         px[k] = pk & 0xFFFFu;
         py[k] = pk >> 16;
-        dvs[k] = load_dir(vimg, a.d.w, a.d.vn, px[k], py[k], v);
+        dvs[k] = load_dir(vimg, a.d.w, vslots, px[k], py[k], vs);
         xmin = min(xmin, px[k]); xmax = max(xmax, px[k]);
         ymin = min(ymin, py[k]); ymax = max(ymax, py[k]);
       }
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     if (a.fc.fast_ok == 0 || weird) {  // rare: whole chunk with the exact predicate
       for (int h = 0; h < hn; ++h) {
         const float2 hp = htrue[h];
-        const int c = exact_count(pix, vimg, a.d.w, a.d.vn, v, t0, npx, hp.x, hp.y, a.fc.thr);
+        const int c = exact_count(pix, vimg, a.d.w, vslots, vs, t0, npx, hp.x, hp.y, a.fc.thr);
         if (lane == 0 && c) atomicAdd(&gc[h], c);
       }
       if (a.ws.stats && lane == 0) atomicAdd(&a.ws.stats[1], (unsigned long long)npx * hn);
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
             const float ax = pa.x - ox, ay = pa.y - oy, bx = pb.x - ox, by = pb.y - oy;  // same h' as the main loop
             const float ea = a.fc.e1 * (oct_norm(ax, ay) + rr), eb = a.fc.e1 * (oct_norm(bx, by) + rr);
             const int2 dd = band_adjust2(cA, cB, npx, ax, ay, bx, by, ea, eb, a.fc.kappa2, hfilt, ha, hb_ok, pix, vimg,
-                                         a.d.w, a.d.vn, v, t0, a.fc.thr, a.ws.stats);
+                                         a.d.w, vslots, vs, t0, a.fc.thr, a.ws.stats);
             if (lane == 0) {
               if (dd.x) atomicAdd(&gc[ha], dd.x);
               if (dd.y) atomicAdd(&gc[ha + 32], dd.y);
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     for (int k = 0; k < nlist; ++k) {
       const int h = a.ws.exact_list[hoff + k];
       const float2 hp = htrue[h];
-      const int c = exact_count(pix, vimg, a.d.w, a.d.vn, v, t0, npx, hp.x, hp.y, a.fc.thr);
+      const int c = exact_count(pix, vimg, a.d.w, vslots, vs, t0, npx, hp.x, hp.y, a.fc.thr);
       if (lane == 0 && c) atomicAdd(&gc[h], c);
     }
   }
@@ -501,7 +505,8 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc, 
   const int tn = ws.job_tn[job];
   const int img = job / d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
-  const float* vimg = vertex + (size_t)img * d.hw * d.vn * 2;
+  const int vslots = d.vn * d.vpc, vs = (d.vpc > 1 ? (job - img * d.oc) * d.vn : 0) + v;
+  const float* vimg = vertex + (size_t)img * d.hw * vslots * 2;
   const float2 wp = ws.win_pts[job * d.vn + v];
   double s[5] = {0, 0, 0, 0, 0};
 #pragma unroll
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc, 
     if (t < tn) {
       const uint32_t pk = pix[t];
       const int x = pk & 0xFFFFu, y = pk >> 16;
-      const float2 dv = load_dir(vimg, d.w, d.vn, x, y, v);
+      const float2 dv = load_dir(vimg, d.w, vslots, x, y, vs);
       const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
       const bool in = exact_inlier(wp.x, wp.y, cx, cy, dv.x, dv.y, exact_norm(dv.x, dv.y), fc.thr);  // :353
       const bool finite = fabsf(dv.x) <= 3.0e38f && fabsf(dv.y) <= 3.0e38f;

@@ -16,12 +16,12 @@ DEBUG_FIELDS = ("tn0", "tn", "rounds", "counts", "win_idx", "hyps", "win_pts", "
 
 
 def _params(b, h, w, oc, vn, round_hyp_num, inlier_thresh, confidence, max_iter, min_num, max_num, seed,
-            image_offset, pix_capacity, force_exact):
+            image_offset, pix_capacity, force_exact, vertex_per_class=False):
     return _lib.RansacParams(
         b=b, h=h, w=w, oc=oc, vn=vn, round_hyp_num=int(round_hyp_num), max_iter=int(max_iter),
         inlier_thresh=float(inlier_thresh), confidence=float(confidence), min_num=float(min_num),
         max_num=float(max_num), seed=int(seed) & 0xFFFFFFFFFFFFFFFF, image_offset=int(image_offset),
-        pix_capacity=int(pix_capacity), force_exact=int(bool(force_exact)), reserved=0)
+        pix_capacity=int(pix_capacity), force_exact=int(bool(force_exact)), vertex_per_class=int(bool(vertex_per_class)))
 
 
 def ransac_voting_layer_all_masks(
@@ -42,10 +42,14 @@ def ransac_voting_layer_all_masks(
     debug_hyps=False,
     pix_capacity=0,
     force_exact=False,
+    seg_scores=False,
 ):
     """
     :param mask:      [b,h,w,oc]   float32 {0,1}
-    :param vertex:    [b,h,w,vn,2] float32 (dy,dx)   (a [b,h,w,vn*2] tensor is viewed as such)
+                      (seg_scores=True: [b,h,w,1+oc] segmentation scores; the one-hot of their arg-max without
+                      the background channel is used, pose_evaluation.py:36-51, without materialising it)
+    :param vertex:    [b,h,w,vn,2] float32 (dy,dx)   (a [b,h,w,vn*2] tensor is viewed as such;
+                      [b,h,w,oc,vn,2] = one field per class, pose_evaluation.py:38-45)
     :param round_hyp_num: hypotheses per round
     :return: [b,oc,vn,2] float32 (x,y) — and a dict of intermediates if return_debug
     """
@@ -54,16 +58,24 @@ def ransac_voting_layer_all_masks(
     if mask.dim() != 4:
         raise ValueError("mask must be [b,h,w,oc], got %s" % (tuple(mask.shape),))
     b, h, w, oc = mask.shape
+    if seg_scores:
+        oc -= 1
+        if oc < 1:
+            raise ValueError("seg scores need at least one object channel")
     if vertex.dim() == 4:
         vertex = vertex.view(b, h, w, vertex.shape[3] // 2, 2)
-    if vertex.dim() != 5 or tuple(vertex.shape[:3]) != (b, h, w) or vertex.shape[4] != 2:
+    vertex_per_class = vertex.dim() == 6
+    if vertex_per_class:
+        if tuple(vertex.shape[:4]) != (b, h, w, oc) or vertex.shape[5] != 2:
+            raise ValueError("per-class vertex must be [b,h,w,oc,vn,2], got %s" % (tuple(vertex.shape),))
+    elif vertex.dim() != 5 or tuple(vertex.shape[:3]) != (b, h, w) or vertex.shape[4] != 2:
         raise ValueError("vertex must be [b,h,w,vn,2] matching mask, got %s" % (tuple(vertex.shape),))
     if vertex.device != mask.device:
         raise ValueError("mask and vertex must be on the same device")
-    vn = vertex.shape[3]
+    vn = vertex.shape[-2]
     dev = mask.device
     p = _params(b, h, w, oc, vn, round_hyp_num, inlier_thresh, confidence, max_iter, min_num, max_num, seed,
-                image_offset, pix_capacity, force_exact)
+                image_offset, pix_capacity, force_exact, vertex_per_class)
     hn, mi = p.round_hyp_num, p.max_iter
     if idxs is not None:
         idxs = as_cuda(idxs, torch.int32, "idxs")
@@ -99,7 +111,8 @@ def ransac_voting_layer_all_masks(
         dbg_struct = _lib.RansacDebug(**{k: ptr(dbg.get(k)) for k in DEBUG_FIELDS})
     hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
     with torch.cuda.device(dev):
-        rc = _lib.lib().casa_ransac_vote(
+        fn = _lib.lib().casa_ransac_vote_seg if seg_scores else _lib.lib().casa_ransac_vote
+        rc = fn(
             hdl, C.byref(p), ptr(mask), ptr(vertex), ptr(idxs), ptr(selection), ptr(out),
             C.byref(dbg_struct) if dbg_struct is not None else None, current_stream_ptr(dev))
     _lib.check(rc)
@@ -133,3 +146,164 @@ def ransac_voting_layer_all_masks_host(mask, vertex, round_hyp_num, inlier_thres
     rc = _lib.lib().casa_ransac_vote_host(hdl, C.byref(p), mask_t.data_ptr(), vertex_t.data_ptr(), out.data_ptr())
     _lib.check(rc)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Post-step on the host: PnP and pose metrics.  The reference leaves TensorFlow here as well
+# (tf.numpy_function -> Python -> OpenCV, ransac_voting.py:513), so this part is numpy + the same cv2 calls.
+# A batched GPU PnP is a "next" row of SURVEY.md section 8(f).
+# ------------------------------------------------------------------------------------------------------------
+import math  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+
+def _np(x, dtype=None):
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    x = np.asarray(x)
+    return x.astype(dtype) if dtype is not None else x
+
+
+def pnp(points_3d, points_2d, camera_matrix, method=None):
+    """ransac_voting.py:13-57: EPnP-RANSAC initialisation, iterative refinement, [R|t] float32 [3,4]."""
+    import cv2
+
+    assert points_3d.shape[0] == points_2d.shape[0], "points 3D and points 2D must have same number of vertices"
+    if np.abs(np.sum(points_2d)) < 1e-4:
+        return np.zeros([3, 4]).astype(np.float32)
+    points_3d = np.expand_dims(points_3d, 0)
+    points_2d = np.expand_dims(points_2d, 0)
+    points_2d = np.ascontiguousarray(points_2d.astype(np.float64))
+    points_3d = np.ascontiguousarray(points_3d.astype(np.float64))
+    camera_matrix = camera_matrix.astype(np.float64)
+    _, rvec0, T0, _ = cv2.solvePnPRansac(points_3d, points_2d, camera_matrix, None, flags=cv2.SOLVEPNP_EPNP,
+                                         confidence=0.9999, reprojectionError=12)
+    ret, R_exp, t = cv2.solvePnP(points_3d, points_2d, camera_matrix, None, flags=cv2.SOLVEPNP_ITERATIVE,
+                                 useExtrinsicGuess=True, rvec=rvec0, tvec=T0)
+    if ret is False or np.isnan(np.sum(t)):
+        return np.zeros([3, 4]).astype(np.float32)
+    R, _ = cv2.Rodrigues(R_exp)
+    if t[2] < 0:
+        t *= -1
+        R *= -1
+    return np.concatenate([R, t], axis=-1).astype(np.float32)
+
+
+def transform_points_back(points, h_crop, w_crop, sx, sy, dx, dy, angle, scale):
+    """transform_points_back_tf (ransac_voting.py:92-121) in float32: undo scale, crop offset, shift and rotation."""
+    f = np.float32
+    proj = (points.astype(f) / f(scale)).astype(f)
+    tm = np.array([[1.0, 0.0, -dx], [0.0, 1.0, -dy], [0.0, 0.0, 1.0]], f)
+    cx, cy = f(sx) / f(2.0), f(sy) / f(2.0)
+    ang = f(-angle) * f(math.pi / 180)
+    a, b = f(np.cos(ang)), f(np.sin(ang))
+    c = (f(1.0) - a) * cx - b * cy
+    d = b * cx + (f(1.0) - a) * cy
+    rm = np.array([[a, b, c], [-b, a, d], [0.0, 0.0, 1.0]], f)
+    proj = proj + np.array([w_crop, h_crop], f)
+    homog = np.concatenate([proj.T, np.ones([1, points.shape[0]], f)], axis=0)
+    new = rm @ (tm @ homog)
+    return new[0:2].T.astype(f)
+
+
+def project(xyz, K, RT):
+    """project_tf (ransac_voting.py:173-182), float32."""
+    f = np.float32
+    xyz_proj = xyz.astype(f) @ RT[:, :3].astype(f).T + RT[:, 3:].astype(f).T
+    uvw = xyz_proj @ K.astype(f).T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xy = uvw[:, :2] / uvw[:, 2:]
+    return xy.astype(f), xyz_proj.astype(f)
+
+
+def estimate_poses(points, keypoints, camera_matrixes, valid_points_filter, offsets):
+    """ransac_voting.py:525-558.
+    :param points:             [b,oc,vn,2]
+    :param keypoints:          [b,oc,ic,vn,3]
+    :param camera_matrixes:    [b,3,3]
+    :param valid_points_filter:[b,oc]
+    :param offsets:            [b,10]
+    :return: poses [b,oc,3,4] float32, false-positive count per object [oc]
+    """
+    points = _np(points, np.float32)
+    keypoints = _np(keypoints, np.float32)
+    camera_matrixes = _np(camera_matrixes, np.float32)
+    valid = _np(valid_points_filter)
+    offsets = _np(offsets, np.float32)
+    b, oc, ic, vn, _ = keypoints.shape
+    poses = np.zeros((b, oc, 3, 4), np.float32)
+    false_positive = np.zeros((b, oc), np.float32)
+    for i in range(b):
+        o = offsets[i]
+        for c in range(oc):
+            pts = points[i, c]
+            if valid[i, c] == 0 and pts.sum(dtype=np.float32) > 0:  # map_false_positive :517-522
+                false_positive[i, c] = 1.0
+            if abs(pts.sum(dtype=np.float32)) < 0.01:  # map_offsets :489, map_pnp :510
+                continue
+            pts = transform_points_back(pts, o[0], o[1], o[8], o[9], o[4], o[5], o[6], o[7])  # :494-504
+            if abs(pts.sum(dtype=np.float32)) < 0.01:
+                continue
+            poses[i, c] = pnp(keypoints[i, c, 0], pts, camera_matrixes[i])  # :513
+    fp = false_positive.sum(axis=0)
+    return poses, (fp[0] if oc == 1 else fp)  # tf.squeeze(:558)
+
+
+def _adds_error(A, B):
+    """ransac_voting.py:596-610: mean-free closest-point distances in float64."""
+    A = A.astype(np.float64)
+    B = B.astype(np.float64)
+    err = (A * A).sum(1)[:, None] - 2 * (A @ B.T) + (B * B).sum(1)[None, :]
+    return np.sqrt(np.abs(err.min(axis=1)) + 1e-5).astype(np.float32)
+
+
+def map_estimates(pose, pose_gt, object_points_3d, camera_matrix, diameter, valid, count, allowed_error_2d):
+    """ransac_voting.py:561-625 -> [err_2d, err_3d, valid_3d, valid_2d, missing, false_positive]."""
+    if valid == 0:
+        if abs(pose.sum(dtype=np.float32)) > 0.0001:
+            return np.array([0, 0, 0, 0, 0, 1], np.float32)
+        return np.zeros(6, np.float32)
+    if abs(pose.sum(dtype=np.float32)) < 0.0001:
+        return np.array([99.9, 999.9, 0.0, 0.0, 1.0, 0.0], np.float32)
+    pts = object_points_3d[0][: int(count[0])]
+    p2d, p3d = project(pts, camera_matrix, pose)
+    t2d, t3d = project(pts, camera_matrix, pose_gt[0])
+    err_2d = np.float32(np.sqrt(((t2d - p2d) ** 2).sum(1)).mean())
+    if int(count[0]) in (7862, 3417):  # glue and eggbox: ADD-S (:618)
+        err_3d = np.float32(_adds_error(t3d, p3d).mean())
+    else:
+        err_3d = np.float32(np.sqrt(((t3d - p3d) ** 2).sum(1)).mean())
+    valid_3d = np.float32(err_3d < np.float32(diameter[0][0]) * np.float32(0.1))
+    valid_2d = np.float32(err_2d < allowed_error_2d)
+    return np.array([err_2d, err_3d, valid_3d, valid_2d, 0.0, 0.0], np.float32)
+
+
+def evaluate_poses(poses, poses_gt, points_estimated, object_points_3d, object_points_3d_count, camera_matrixes,
+                   diameters, valid_points_filter, allowed_error_2d):
+    """ransac_voting.py:628-687 -> (err_2d, err_3d, valid_2d, valid_3d, missing_object, valid_points_count,
+    false_positive_detection), each summed over the batch -> [oc]."""
+    poses = _np(poses, np.float32)
+    poses_gt = _np(poses_gt, np.float32)
+    object_points_3d = _np(object_points_3d, np.float32)
+    counts = _np(object_points_3d_count)
+    cams = _np(camera_matrixes, np.float32)
+    diameters = _np(diameters, np.float32)
+    valid = _np(valid_points_filter)
+    b, oc, ic, vn, _ = object_points_3d.shape
+    dm = diameters.reshape(-1)  # tf.reshape(diameters, [-1, ic, 1]) (:651); also accept per-object diameters
+    if dm.size == b * oc * ic:
+        diameters = dm.reshape(b, oc, ic, 1)
+    elif dm.size == oc * ic:
+        diameters = np.broadcast_to(dm.reshape(1, oc, ic, 1), (b, oc, ic, 1))
+    elif dm.size == oc:
+        diameters = np.broadcast_to(dm.reshape(1, oc, 1, 1), (b, oc, ic, 1))
+    else:
+        raise ValueError("diameters must hold b*oc*ic, oc*ic or oc values")
+    res = np.zeros((b, oc, 6), np.float32)
+    for i in range(b):
+        for c in range(oc):
+            res[i, c] = map_estimates(poses[i, c], poses_gt[i, c], object_points_3d[i, c], cams[i], diameters[i, c],
+                                      valid[i, c], counts[i, c], allowed_error_2d)
+    s = res.sum(axis=0)
+    return s[:, 0], s[:, 1], s[:, 3], s[:, 2], s[:, 4], valid.sum(axis=0).astype(np.float32), s[:, 5]

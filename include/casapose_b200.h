@@ -76,7 +76,8 @@ typedef struct casa_ransac_params {
                           /* random numbers as the unsharded one)                           */
   int32_t pix_capacity;   /* per-image pixel-list capacity; 0 = h*w (enough for one-hot)    */
   int32_t force_exact;    /* 1 = disable the filtered predicate (tests only)                */
-  int32_t reserved;
+  int32_t vertex_per_class; /* 0: vertex is [b,h,w,vn,2]; 1: [b,h,w,oc,vn,2] (PVNet-style, one field per class;  */
+                            /* pose_evaluation.py:38-45 gathers the arg-max class's vectors)              */
 } casa_ransac_params;
 
 /*
@@ -118,6 +119,16 @@ size_t casa_ransac_workspace_bytes(const casa_ransac_params* p);
 int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, const float* mask,
                      const float* vertex, const int32_t* idxs, const float* selection,
                      float* out_points, const casa_ransac_debug* debug, void* stream);
+
+/*
+ * Fused pre-step of estimate_and_evaluate_poses / pose_estimation
+ * (/root/reference/casapose/pose_estimation/pose_evaluation.py:36-47, 241-252):
+ *   mask = one_hot(argmax(output_seg, 3))[..., 1:]   without materialising the float one-hot.
+ *   seg  device float32 [b,h,w,1+oc] segmentation scores (arg-max takes the first maximum)
+ */
+int casa_ransac_vote_seg(casa_handle* h, const casa_ransac_params* p, const float* seg,
+                         const float* vertex, const int32_t* idxs, const float* selection,
+                         float* out_points, const casa_ransac_debug* debug, void* stream);
 
 /*
  * Same call with HOST buffers: copies mask/vertex host->device (pipelined per image),

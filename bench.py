@@ -152,7 +152,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from casapose_b200 import _lib
+    from casapose_b200 import _lib, sharding
     from casapose_b200.pose_estimation.ransac_voting import (ransac_voting_layer_all_masks,
                                                                ransac_voting_layer_all_masks_host)
 
@@ -178,17 +178,13 @@ def main():
     vertex_h = torch.from_numpy(d["vertex"]).pin_memory()
     mask = mask_h.to(dev, non_blocking=True)
     vertex = vertex_h.to(dev, non_blocking=True)
-    gathered = torch.empty((world * B, OC, VN, 2), dtype=torch.float32, device=dev)
     lib = _lib.lib()
     hdl = _lib.handle(local)
     in_bytes = mask.numel() * 4 + vertex.numel() * 4
 
     def step(seed):
-        pts = ransac_voting_layer_all_masks(mask, vertex, HN, seed=seed, image_offset=rank * B)
-        if distributed:
-            dist.all_gather_into_tensor(gathered, pts)
-            return gathered
-        return pts
+        # this rank's B images of the global batch of world*B, then the NCCL all-gather of the keypoints
+        return sharding.sharded_vote(ransac_voting_layer_all_masks, mask, vertex, HN, n_images=world * B, seed=seed)
 
     def barrier():
         if distributed:

@@ -36,7 +36,7 @@ FLOP_PER_UNIT = 11
 METRIC = "keypoint-voting frames/s (480x640, 8 obj x 9 kp, 512 hyp)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch on this workload,
 # from profiles/r01_k_score_full.txt (ncu --set full); null until a capture exists
-K_SCORE_DRAM_BYTES = 56.3e6
+K_SCORE_DRAM_BYTES = 56.0e6
 
 
 def parse():

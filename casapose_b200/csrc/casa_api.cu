@@ -98,7 +98,7 @@ namespace {
 
 struct Layout {
   Dims d;
-  size_t off_bits, off_tile_cnt, off_tile_base, off_pix, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
+  size_t off_bits, off_tile_cnt, off_tile_base, off_pix, off_vdir, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
       off_job_rounds, off_job_selthr, off_win_ratio, off_win_pts, off_hyp_true, off_hyp_filt, off_exact_list,
       off_n_exact, off_counts, off_item_start, off_rtile_start, off_ctrl, off_partial, off_stats, total;
 };
@@ -145,6 +145,7 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   L.off_tile_cnt = bump(cur, J * d.nct * 4);
   L.off_tile_base = bump(cur, J * d.nct * 4);
   L.off_pix = bump(cur, (size_t)d.b * d.cap * 4);
+  L.off_vdir = bump(cur, (size_t)d.b * d.cap * d.vn * 8);
   L.off_job_tn0 = bump(cur, J * 4);
   L.off_job_tn = bump(cur, J * 4);
   L.off_job_off = bump(cur, J * 4);
@@ -174,6 +175,7 @@ WS make_ws(const Layout& L, void* base, bool stats) {
   w.tile_cnt = (int*)(b + L.off_tile_cnt);
   w.tile_base = (int*)(b + L.off_tile_base);
   w.pix = (uint32_t*)(b + L.off_pix);
+  w.vdir = (float2*)(b + L.off_vdir);
   w.job_tn0 = (int*)(b + L.off_job_tn0);
   w.job_tn = (int*)(b + L.off_job_tn);
   w.job_off = (int*)(b + L.off_job_off);
@@ -266,18 +268,22 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     k_cap_filter<<<d.J, 1024, 0, st>>>(ws, d, selection);
     ++launches;
   }
+  {
+    const int gx = (d.cap + 255) / 256 < 160 ? (d.cap + 255) / 256 : 160;
+    k_gather_dirs<<<dim3(gx, d.b), 256, 0, st>>>(vertex, ws, d);
+    ++launches;
+  }
   CUDA_TRY(cudaGetLastError());
 
   ScoreArgs sa;
   sa.ws = ws;
   sa.d = d;
   sa.fc = fc;
-  sa.vertex = vertex;
   k_init_jobs<<<(d.J + 255) / 256, 256, 0, st>>>(ws, d);
   ++launches;
   const int upd_threads = 32 * ((d.vn + 0) > 0 ? d.vn : 1);
   for (int rnd = 0; rnd < d.max_iter; ++rnd) {
-    k_hypgen<<<dim3((d.hn * d.vn + 255) / 256, d.J), 256, 0, st>>>(ws, d, fc, vertex, idxs, rnd, dbg.hyps);
+    k_hypgen<<<dim3((d.hn * d.vn + 255) / 256, d.J), 256, 0, st>>>(ws, d, fc, idxs, rnd, dbg.hyps);
     k_plan<<<1, 1024, 0, st>>>(ws, d, rnd);
     CUDA_TRY(cudaGetLastError());
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
@@ -302,7 +308,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   }
   const int n_rtiles = h->pinned[CTRL_NRTILES];  // read back with the loop's exit flag
   if (n_rtiles > 0) {
-    k_refine<<<dim3(n_rtiles, d.vn), 256, 0, st>>>(ws, d, fc, vertex);
+    k_refine<<<dim3(n_rtiles, d.vn), 256, 0, st>>>(ws, d, fc);
     ++launches;
   }
   k_solve<<<d.J, 32, 0, st>>>(ws, d, out_points, dbg);
@@ -330,6 +336,18 @@ extern "C" int casa_ransac_vote_seg(casa_handle* h, const casa_ransac_params* p,
   return ransac_vote_impl(h, p, seg, 1, vertex, idxs, selection, out_points, debug, stream);
 }
 
+// true if `p` is page-locked host memory the device can read directly (UVA: same pointer)
+static bool host_pointer_is_mapped(const void* p, const void** dev_ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return false;
+  *dev_ptr = at.devicePointer;
+  return true;
+}
+
 extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
                                      const float* vertex_host, float* out_points_host) {
   if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
@@ -339,18 +357,28 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t hw = (size_t)p->h * p->w;
-  const size_t mask_b = ((size_t)p->b * hw * p->oc * 4 + 255) & ~size_t(255);
   const size_t vfields = p->vertex_per_class ? (size_t)p->oc : 1;
-  const size_t vert_b = ((size_t)p->b * hw * vfields * p->vn * 2 * 4 + 255) & ~size_t(255);
+  const size_t mask_n = (size_t)p->b * hw * p->oc * 4, vert_n = (size_t)p->b * hw * vfields * p->vn * 2 * 4;
   const size_t out_b = (size_t)p->b * p->oc * p->vn * 2 * 4;
+  cudaStream_t st = h->own_stream;
+  // Pinned (page-locked) host buffers are read by the kernels directly: the mask is streamed once by
+  // k_mask_bits and only the masked pixels' rows of the vector field are fetched by k_gather_dirs, so
+  // about 200 MB instead of 511 MB cross PCIe for a 16-frame batch.  Pageable buffers are staged.
+  const void *dm = nullptr, *dv = nullptr;
+  const bool zero_copy = !getenv("CASA_NO_ZERO_COPY") && host_pointer_is_mapped(mask_host, &dm) && host_pointer_is_mapped(vertex_host, &dv);
+  const size_t mask_b = zero_copy ? 0 : (mask_n + 255) & ~size_t(255);
+  const size_t vert_b = zero_copy ? 0 : (vert_n + 255) & ~size_t(255);
   rc = ensure(&h->io_mem, &h->io_bytes, mask_b + vert_b + out_b);
   if (rc) return rc;
-  float* dmask = (float*)h->io_mem;
-  float* dvert = (float*)((char*)h->io_mem + mask_b);
+  const float* dmask = (const float*)dm;
+  const float* dvert = (const float*)dv;
   float* dout = (float*)((char*)h->io_mem + mask_b + vert_b);
-  cudaStream_t st = h->own_stream;
-  CUDA_TRY(cudaMemcpyAsync(dmask, mask_host, (size_t)p->b * hw * p->oc * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(dvert, vertex_host, (size_t)p->b * hw * vfields * p->vn * 2 * 4, cudaMemcpyHostToDevice, st));
+  if (!zero_copy) {
+    CUDA_TRY(cudaMemcpyAsync(h->io_mem, mask_host, mask_n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync((char*)h->io_mem + mask_b, vertex_host, vert_n, cudaMemcpyHostToDevice, st));
+    dmask = (const float*)h->io_mem;
+    dvert = (const float*)((char*)h->io_mem + mask_b);
+  }
   rc = casa_ransac_vote(h, p, dmask, dvert, nullptr, nullptr, dout, nullptr, (void*)st);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));

@@ -49,6 +49,8 @@ struct WS {
   int* tile_cnt;       // [b][oc][nct]   per count-tile class counts
   int* tile_base;      // [b][oc][nct]   exclusive prefix of tile_cnt
   uint32_t* pix;       // [b][cap]       compacted pixel lists, (y<<16|x), raster order per class
+  float2* vdir;        // [b][cap*vn]    compacted directions (dy,dx): job j, keypoint v, pixel t at
+                       //                (img*cap + job_off[j])*vn + v*tn[j] + t  — gathered once per call
   int* job_tn0;        // [J]
   int* job_tn;         // [J]
   int* job_off;        // [J]

@@ -250,4 +250,31 @@ __global__ void __launch_bounds__(1024) k_cap_filter(WS ws, Dims d, const float*
   }
 }
 
+// Gathers the (dy,dx) vectors of every listed pixel ONCE into the compacted, keypoint-major buffer all
+// later kernels read (direct = boolean_mask(vertex, mask), ransac_voting.py:308; for PVNet-style outputs
+// the class's own field, pose_evaluation.py:38-45).  One thread per listed pixel: the pixel's 8*vn-byte
+// row is read once (the only access to `vertex`, which may be device memory or mapped pinned host
+// memory — then only masked pixels of the field cross PCIe), the writes are coalesced per keypoint.
+__global__ void __launch_bounds__(256) k_gather_dirs(const float* __restrict__ vertex, WS ws, Dims d) {
+  const int img = blockIdx.y;
+  const int vslots = d.vn * d.vpc;
+  const float* vimg = vertex + (size_t)img * d.hw * vslots * 2;
+  const int last = img * d.oc + d.oc - 1;
+  const int total = ws.job_off[last] + ws.job_tn0[last];  // end of the image's lists (before the cap)
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < total; p += gridDim.x * 256) {
+    int c = 0;
+    for (int k = 1; k < d.oc; ++k)
+      if (ws.job_off[img * d.oc + k] <= p) c = k;
+    const int job = img * d.oc + c;
+    const int off = ws.job_off[job], tn = ws.job_tn[job];
+    const int t = p - off;
+    if (t >= tn || (ws.job_flags[job] & JOB_GATED)) continue;
+    const uint32_t pk = ws.pix[(size_t)img * d.cap + p];
+    const int x = pk & 0xFFFFu, y = pk >> 16;
+    const float2* row = reinterpret_cast<const float2*>(vimg + ((size_t)(y * d.w + x) * vslots + (d.vpc > 1 ? c * d.vn : 0)) * 2);
+    float2* dst = ws.vdir + ((size_t)img * d.cap + off) * d.vn + t;
+    for (int v = 0; v < d.vn; ++v) dst[(size_t)v * tn] = __ldg(row + v);
+  }
+}
+
 }  // namespace casa

@@ -16,12 +16,16 @@
 
 namespace casa {
 
-// vertex[img, y, x, (field,) v, 0:2] = (dy, dx)  ->  (dx, dy) like tf.reverse(..., axis=[2]) at :308.
-// `vn` here is the number of keypoint slots per pixel row (vn * fields) and `v` the slot (field * vn + v):
-// callers fold the per-class field of PVNet-style outputs (pose_evaluation.py:38-45) into both.
-__device__ __forceinline__ float2 load_dir(const float* __restrict__ vimg, int w, int vn, int x, int y, int v) {
-  const float2 t = __ldg(reinterpret_cast<const float2*>(vimg + ((size_t)(y * w + x) * vn + v) * 2));
-  return make_float2(t.y, t.x);
+// Directions come from the compacted buffer written by k_gather_dirs: `vd` points at the array of one
+// (job, keypoint), indexed by the pixel's position t in the job's list.  Stored (dy, dx) like the network
+// output; returned as (dx, dy) like tf.reverse(..., axis=[2]) at :308.
+__device__ __forceinline__ float2 load_dir(const float2* __restrict__ vd, int t) {
+  const float2 s = __ldg(vd + t);
+  return make_float2(s.y, s.x);
+}
+
+__device__ __forceinline__ const float2* job_dirs(const WS& ws, const Dims& d, int img, int job, int tn, int v) {
+  return ws.vdir + ((size_t)img * d.cap + ws.job_off[job]) * d.vn + (size_t)v * tn;
 }
 
 // ------------------------------------------------------------------------------------ init
@@ -41,8 +45,8 @@ __global__ void __launch_bounds__(256) k_init_jobs(WS ws, Dims d) {
 
 // ------------------------------------------------------------------------------------ K2
 // grid (ceil(hn*vn/256), J): one thread per (hypothesis, keypoint) of an active job
-__global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, const float* __restrict__ vertex,
-                                                const int32_t* __restrict__ idxs, int rnd, float* dbg_hyps) {
+__global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, const int32_t* __restrict__ idxs, int rnd,
+                                                float* dbg_hyps) {
   const int job = blockIdx.y;
   if (!(ws.job_flags[job] & JOB_ACTIVE)) return;
   const int e = blockIdx.x * 256 + threadIdx.x;
@@ -51,8 +55,7 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
   const int img = job / d.oc, cls = job - img * d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
   const int h = e / d.vn, v = e - h * d.vn;
-  const int vslots = d.vn * d.vpc, vs = (d.vpc > 1 ? cls * d.vn : 0) + v;
-  const float* vimg = vertex + (size_t)img * d.hw * vslots * 2;
+  const float2* vd = job_dirs(ws, d, img, job, tn, v);
   int2 ip;
   if (idxs) {
     const int32_t* src = idxs + ((((size_t)job * d.max_iter + rnd) * d.hn + h) * d.vn + v) * 2;
@@ -70,8 +73,8 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
   const int x0 = p0 & 0xFFFFu, y0 = p0 >> 16, x1 = p1 & 0xFFFFu, y1 = p1 >> 16;
   const float2 c0 = make_float2((float)x0 + 0.5f, (float)y0 + 0.5f);  // :306
   const float2 c1 = make_float2((float)x1 + 0.5f, (float)y1 + 0.5f);
-  const float2 d0 = load_dir(vimg, d.w, vslots, x0, y0, vs);
-  const float2 d1 = load_dir(vimg, d.w, vslots, x1, y1, vs);
+  const float2 d0 = load_dir(vd, ip.x);
+  const float2 d1 = load_dir(vd, ip.y);
   const float2 hp = exact_hypothesis(c0, c1, d0, d1);
   const size_t o = ((size_t)job * d.vn + v) * d.hn + h;
   ws.hyp_true[o] = hp;
@@ -156,20 +159,19 @@ struct ScoreArgs {
   WS ws;
   Dims d;
   FilterConsts fc;
-  const float* vertex;
 };
 
 constexpr int kHypPerLane = 8;
 
 // Exact inlier count of one hypothesis over pixels [t0, t0+npx) of a job, whole warp cooperating.
-__device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const float* __restrict__ vimg, int w, int vn,
-                                        int v, int t0, int npx, float hx, float hy, float thr) {
+__device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const float2* __restrict__ vd, int t0, int npx,
+                                        float hx, float hy, float thr) {
   const int lane = threadIdx.x & 31;
   int c = 0;
   for (int q = lane; q < npx; q += 32) {
     const uint32_t pk = pix[t0 + q];
     const int x = pk & 0xFFFFu, y = pk >> 16;
-    const float2 dv = load_dir(vimg, w, vn, x, y, v);
+    const float2 dv = load_dir(vd, t0 + q);
     c += exact_inlier(hx, hy, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y, exact_norm(dv.x, dv.y), thr) ? 1 : 0;
   }
   return __reduce_add_sync(0xffffffffu, c);
@@ -189,8 +191,8 @@ __device__ __forceinline__ float oct_norm(float x, float y) {
 __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
                                              float ax, float ay, float bx, float by, float ea, float eb, float kappa2,
                                              const float2* __restrict__ hfilt, int ha, int hb_ok,
-                                             const uint32_t* __restrict__ pix, const float* __restrict__ vimg, int w,
-                                             int vn, int v, int t0, float thr, unsigned long long* stats) {
+                                             const uint32_t* __restrict__ pix, const float2* __restrict__ vd, int t0,
+                                             float thr, unsigned long long* stats) {
   const int lane = threadIdx.x & 31;
   int da = 0, db = 0;
   for (int q = lane; q < npx; q += 32) {
@@ -205,7 +207,7 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
     if (ua || ub) {  // ~1e-5 of the units
       const uint32_t pk = pix[t0 + q];
       const int x = pk & 0xFFFFu, y = pk >> 16;
-      const float2 dv = load_dir(vimg, w, vn, x, y, v);
+      const float2 dv = load_dir(vd, t0 + q);
       const float nd = exact_norm(dv.x, dv.y);
       if (ua) {
         const float2 h = hfilt[ha];
@@ -266,8 +268,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     const int img = job / a.d.oc;
     const int tn = a.ws.job_tn[job];
     const uint32_t* pix = a.ws.pix + (size_t)img * a.d.cap + a.ws.job_off[job];
-    const int vslots = a.d.vn * a.d.vpc, vs = (a.d.vpc > 1 ? (job - img * a.d.oc) * a.d.vn : 0) + v;
-    const float* vimg = a.vertex + (size_t)img * a.d.hw * vslots * 2;
+    const float2* vd = job_dirs(a.ws, a.d, img, job, tn, v);
     const int t0 = chunk * kChunk;
     const int npx = min(kChunk, tn - t0);
 
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
         const uint32_t pk = pix[t0 + q];
         px[k] = pk & 0xFFFFu;
         py[k] = pk >> 16;
-        dvs[k] = load_dir(vimg, a.d.w, vslots, px[k], py[k], vs);
+        dvs[k] = load_dir(vd, t0 + q);
         xmin = min(xmin, px[k]); xmax = max(xmax, px[k]);
         ymin = min(ymin, py[k]); ymax = max(ymax, py[k]);
       }
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     if (a.fc.fast_ok == 0 || weird) {  // rare: whole chunk with the exact predicate
       for (int h = 0; h < hn; ++h) {
         const float2 hp = htrue[h];
-        const int c = exact_count(pix, vimg, a.d.w, vslots, vs, t0, npx, hp.x, hp.y, a.fc.thr);
+        const int c = exact_count(pix, vd, t0, npx, hp.x, hp.y, a.fc.thr);
         if (lane == 0 && c) atomicAdd(&gc[h], c);
       }
       if (a.ws.stats && lane == 0) atomicAdd(&a.ws.stats[1], (unsigned long long)npx * hn);
@@ -389,8 +390,8 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
             const float2 pb = hb_ok ? hfilt[ha + 32] : make_float2(qnan, qnan);
             const float ax = pa.x - ox, ay = pa.y - oy, bx = pb.x - ox, by = pb.y - oy;  // same h' as the main loop
             const float ea = a.fc.e1 * (oct_norm(ax, ay) + rr), eb = a.fc.e1 * (oct_norm(bx, by) + rr);
-            const int2 dd = band_adjust2(cA, cB, npx, ax, ay, bx, by, ea, eb, a.fc.kappa2, hfilt, ha, hb_ok, pix, vimg,
-                                         a.d.w, vslots, vs, t0, a.fc.thr, a.ws.stats);
+            const int2 dd = band_adjust2(cA, cB, npx, ax, ay, bx, by, ea, eb, a.fc.kappa2, hfilt, ha, hb_ok, pix, vd,
+                                         t0, a.fc.thr, a.ws.stats);
             if (lane == 0) {
               if (dd.x) atomicAdd(&gc[ha], dd.x);
               if (dd.y) atomicAdd(&gc[ha + 32], dd.y);
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     for (int k = 0; k < nlist; ++k) {
       const int h = a.ws.exact_list[hoff + k];
       const float2 hp = htrue[h];
-      const int c = exact_count(pix, vimg, a.d.w, vslots, vs, t0, npx, hp.x, hp.y, a.fc.thr);
+      const int c = exact_count(pix, vd, t0, npx, hp.x, hp.y, a.fc.thr);
       if (lane == 0 && c) atomicAdd(&gc[h], c);
     }
   }
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(512) k_update(WS ws, Dims d, int rnd, casa_ran
 // Re-votes the winner (:353) and accumulates the normal equations (:356-362): float32 products exactly
 // as the reference forms them (normal * inlier flag, so a non-finite direction poisons the sums as it
 // does there), float64 accumulation, fixed reduction order.
-__global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc, const float* __restrict__ vertex) {
+__global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc) {
   const int rt = blockIdx.x, v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int lo = 0, hi = d.J;
   while (hi - lo > 1) {
@@ -505,8 +506,7 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc, 
   const int tn = ws.job_tn[job];
   const int img = job / d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
-  const int vslots = d.vn * d.vpc, vs = (d.vpc > 1 ? (job - img * d.oc) * d.vn : 0) + v;
-  const float* vimg = vertex + (size_t)img * d.hw * vslots * 2;
+  const float2* vd = job_dirs(ws, d, img, job, tn, v);
   const float2 wp = ws.win_pts[job * d.vn + v];
   double s[5] = {0, 0, 0, 0, 0};
 #pragma unroll
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc, 
     if (t < tn) {
       const uint32_t pk = pix[t];
       const int x = pk & 0xFFFFu, y = pk >> 16;
-      const float2 dv = load_dir(vimg, d.w, vslots, x, y, vs);
+      const float2 dv = load_dir(vd, t);
       const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
       const bool in = exact_inlier(wp.x, wp.y, cx, cy, dv.x, dv.y, exact_norm(dv.x, dv.y), fc.thr);  // :353
       const bool finite = fabsf(dv.x) <= 3.0e38f && fabsf(dv.y) <= 3.0e38f;

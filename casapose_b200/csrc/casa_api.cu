@@ -255,7 +255,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   h->score_ms = 0.0;
   h->score_launches = 0;
 
-  const int vec4 = ((d.oc & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
+  const int vec4 = ((((size_t)d.hw * d.oc) & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
   if (mask_is_seg)
     k_seg_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d);
   else
@@ -269,8 +269,11 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     ++launches;
   }
   {
-    const int gx = (d.cap + 255) / 256 < 160 ? (d.cap + 255) / 256 : 160;
-    k_gather_dirs<<<dim3(gx, d.b), 256, 0, st>>>(vertex, ws, d);
+    const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
+    if (d.vn == 9)
+      k_gather_dirs<18><<<dim3(gx, d.J), 256, 0, st>>>(vertex, ws, d);
+    else
+      k_gather_dirs<0><<<dim3(gx, d.J), 256, 0, st>>>(vertex, ws, d);
     ++launches;
   }
   CUDA_TRY(cudaGetLastError());

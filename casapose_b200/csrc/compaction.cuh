@@ -18,41 +18,72 @@
 
 namespace casa {
 
+// Vectorised path (tile slab 16-byte aligned, i.e. (h*w*oc) % 4 == 0 and an aligned base): the block streams its
+// tile's [1024 x oc] floats as one contiguous run of 128-bit loads — every warp-load is 512 contiguous bytes,
+// all oc loads of a thread are independent and in flight together (this matters when `mask` is mapped pinned
+// host memory: full-line PCIe reads) — and ORs the few non-zero elements into a shared-memory word per pixel.
 __global__ void __launch_bounds__(256) k_mask_bits(const float* __restrict__ mask, WS ws, Dims d, int vec4) {
   const int img = blockIdx.y, tile = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   __shared__ int scnt[32];
+  __shared__ unsigned sbits[kCountTile];
   if (tid < 32) scnt[tid] = 0;
-  __syncthreads();
   const float* mimg = mask + (size_t)img * d.hw * d.oc;
+  const int p0 = tile * kCountTile;
+  const int npx = min(kCountTile, d.hw - p0);
   bool bad = false;
+  uint32_t m[4] = {0u, 0u, 0u, 0u};
+  if (vec4) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int p = tile * kCountTile + k * 256 + tid;
-    uint32_t m = 0;
-    if (p < d.hw) {
-      const float* row = mimg + (size_t)p * d.oc;
-      if (vec4) {
-        for (int c4 = 0; c4 < d.oc; c4 += 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(row + c4));
-          m |= (uint32_t)(v.x != 0.f) << c4;
-          m |= (uint32_t)(v.y != 0.f) << (c4 + 1);
-          m |= (uint32_t)(v.z != 0.f) << (c4 + 2);
-          m |= (uint32_t)(v.w != 0.f) << (c4 + 3);
-          bad |= (v.x != 0.f && v.x != 1.f) || (v.y != 0.f && v.y != 1.f) || (v.z != 0.f && v.z != 1.f) ||
-                 (v.w != 0.f && v.w != 1.f);
+    for (int k = 0; k < 4; ++k) sbits[k * 256 + tid] = 0u;
+    __syncthreads();
+    const float4* slab = reinterpret_cast<const float4*>(mimg + (size_t)p0 * d.oc);
+    const int n4 = npx * d.oc / 4;  // npx*oc is a multiple of 4 on this path
+    for (int i0 = 0; i0 < n4; i0 += 256 * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 256 + tid;
+        v[u] = i < n4 ? __ldg(slab + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const int e0 = (i0 + u * 256 + tid) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (f[j] != 0.f) {  // NaN != 0 is true, like tf.not_equal (:304)
+            const int e = e0 + j, px = e / d.oc;
+            atomicOr(&sbits[px], 1u << (e - px * d.oc));
+            bad |= f[j] != 1.f;
+          }
         }
-      } else {
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = sbits[k * 256 + tid];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = p0 + k * 256 + tid;
+      if (p < d.hw) {
+        const float* row = mimg + (size_t)p * d.oc;
         for (int c = 0; c < d.oc; ++c) {
           const float v = __ldg(row + c);
-          m |= (uint32_t)(v != 0.f) << c;
+          m[k] |= (uint32_t)(v != 0.f) << c;
           bad |= (v != 0.f && v != 1.f);
         }
       }
-      ws.bits[(size_t)img * d.hw + p] = m;
     }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = p0 + k * 256 + tid;
+    if (p < d.hw) ws.bits[(size_t)img * d.hw + p] = m[k];
     for (int c = 0; c < d.oc; ++c) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
+      const unsigned bal = __ballot_sync(0xffffffffu, (m[k] >> c) & 1u);
       if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
     }
   }
@@ -255,25 +286,42 @@ __global__ void __launch_bounds__(1024) k_cap_filter(WS ws, Dims d, const float*
 // the class's own field, pose_evaluation.py:38-45).  One thread per listed pixel: the pixel's 8*vn-byte
 // row is read once (the only access to `vertex`, which may be device memory or mapped pinned host
 // memory — then only masked pixels of the field cross PCIe), the writes are coalesced per keypoint.
+template <int ROWF>  // floats per pixel row when known at compile time (18 for vn = 9), 0 = runtime
 __global__ void __launch_bounds__(256) k_gather_dirs(const float* __restrict__ vertex, WS ws, Dims d) {
-  const int img = blockIdx.y;
+  const int job = blockIdx.y, img = job / d.oc, cls = job - img * d.oc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tn = ws.job_tn[job];
+  if (tn <= 0 || (ws.job_flags[job] & JOB_GATED)) return;
   const int vslots = d.vn * d.vpc;
-  const float* vimg = vertex + (size_t)img * d.hw * vslots * 2;
-  const int last = img * d.oc + d.oc - 1;
-  const int total = ws.job_off[last] + ws.job_tn0[last];  // end of the image's lists (before the cap)
-  for (int p = blockIdx.x * 256 + threadIdx.x; p < total; p += gridDim.x * 256) {
-    int c = 0;
-    for (int k = 1; k < d.oc; ++k)
-      if (ws.job_off[img * d.oc + k] <= p) c = k;
-    const int job = img * d.oc + c;
-    const int off = ws.job_off[job], tn = ws.job_tn[job];
-    const int t = p - off;
-    if (t >= tn || (ws.job_flags[job] & JOB_GATED)) continue;
-    const uint32_t pk = ws.pix[(size_t)img * d.cap + p];
-    const int x = pk & 0xFFFFu, y = pk >> 16;
-    const float2* row = reinterpret_cast<const float2*>(vimg + ((size_t)(y * d.w + x) * vslots + (d.vpc > 1 ? c * d.vn : 0)) * 2);
-    float2* dst = ws.vdir + ((size_t)img * d.cap + off) * d.vn + t;
-    for (int v = 0; v < d.vn; ++v) dst[(size_t)v * tn] = __ldg(row + v);
+  const int rowf = ROWF ? ROWF : 2 * d.vn;  // floats fetched per pixel (<= 32)
+  const float* vfield = vertex + (size_t)img * d.hw * vslots * 2 + (d.vpc > 1 ? cls * d.vn * 2 : 0);
+  const int off = ws.job_off[job];
+  const uint32_t* pix = ws.pix + (size_t)img * d.cap + off;
+  float2* dst0 = ws.vdir + ((size_t)img * d.cap + off) * d.vn;
+  __shared__ float srow[8][32][33];  // [warp][pixel][float], padded
+  const int nwarps = gridDim.x * 8;
+  for (int base = (blockIdx.x * 8 + warp) * 32; base < tn; base += nwarps * 32) {
+    const int t = base + lane;  // lane l owns list position base + l
+    int rowoff = -1;            // float offset of the pixel's row inside the image's field
+    if (t < tn) {
+      const uint32_t pk = pix[t];
+      rowoff = (int)((pk >> 16) * (uint32_t)d.w + (pk & 0xFFFFu)) * vslots * 2;
+    }
+    // flattened fetch: element e = lane + 32 k of the warp's [32 pixels x rowf floats] block.  Consecutive
+    // lanes read consecutive floats of one row and run on into the next pixel's row, which is contiguous in
+    // memory whenever the two pixels are neighbours — so most warp-loads are one full 128-byte line, and all
+    // rowf loads of a lane are independent (no per-pixel serialisation).
+#pragma unroll 6
+    for (int k = 0; k < rowf; ++k) {
+      const int e = k * 32 + lane;
+      const int src = e / rowf, f = e - src * rowf;
+      const int ro = __shfl_sync(0xffffffffu, rowoff, src);
+      if (ro >= 0) srow[warp][src][f] = __ldg(vfield + ro + f);
+    }
+    __syncwarp();
+    if (t < tn)
+      for (int v = 0; v < d.vn; ++v) dst0[(size_t)v * tn + t] = make_float2(srow[warp][lane][2 * v], srow[warp][lane][2 * v + 1]);
+    __syncwarp();
   }
 }
 

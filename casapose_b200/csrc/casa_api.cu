@@ -40,7 +40,7 @@ struct casa_handle {
   size_t io_bytes = 0;
   int* pinned = nullptr;   // CTRL_WORDS ints, page-locked
   cudaStream_t own_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_round = nullptr;
   uint32_t last_status = 0;
   int64_t last_launches = 0;
   int timing = 0;
@@ -72,6 +72,7 @@ extern "C" int casa_create(int device, casa_handle** out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_round, cudaEventDisableTiming));
   const char* sp = getenv("CASA_SCORE_MINB");
   if (sp && atoi(sp) == 4) h->score_p = 4;
   *out = h;
@@ -88,6 +89,7 @@ extern "C" int casa_destroy(casa_handle* h) {
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_round) cudaEventDestroy(h->ev_round);
   delete h;
   return CASA_OK;
 }
@@ -282,12 +284,11 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   sa.ws = ws;
   sa.d = d;
   sa.fc = fc;
-  k_init_jobs<<<(d.J + 255) / 256, 256, 0, st>>>(ws, d);
-  ++launches;
-  const int upd_threads = 32 * ((d.vn + 0) > 0 ? d.vn : 1);
+  const int upd_threads = 32 * d.vn;
+  const int refine_gx = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
   for (int rnd = 0; rnd < d.max_iter; ++rnd) {
-    k_hypgen<<<dim3((d.hn * d.vn + 255) / 256, d.J), 256, 0, st>>>(ws, d, fc, idxs, rnd, dbg.hyps);
     k_plan<<<1, 1024, 0, st>>>(ws, d, rnd);
+    k_hypgen<<<dim3((d.hn * d.vn + 255) / 256, d.J), 256, 0, st>>>(ws, d, fc, idxs, rnd, dbg.hyps);
     CUDA_TRY(cudaGetLastError());
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     rc = h->score_p == 4 ? launch_score<4>(h, sa, st) : launch_score<3>(h, sa, st);
@@ -296,10 +297,17 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     k_update<<<d.J, upd_threads, 0, st>>>(ws, d, rnd, dbg);
     launches += 4;
     CUDA_TRY(cudaGetLastError());
-    // the reference's data-dependent `while` (:318): one 32-byte read-back per round
+    // the reference's data-dependent `while` (:318): one 32-byte read-back per round.  Refinement and solve are
+    // enqueued BEFORE the host waits, so in the common single-round case the GPU never idles on the round trip;
+    // if another round turns out to be needed they are simply run again after it (they only read loop state).
     CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h->pinned_stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(h->ev_round, st));
+    k_refine<<<dim3(refine_gx, d.vn), 256, 0, st>>>(ws, d, fc);
+    k_solve<<<d.J, 32, 0, st>>>(ws, d, out_points, dbg);
+    launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventSynchronize(h->ev_round));  // the host waits for the loop state only, not for refine/solve
     ++h->score_launches;
     if (h->timing) {
       float ms = 0.f;
@@ -309,13 +317,6 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     for (int k = 0; k < 4; ++k) h->stats[k] = h->pinned_stats[k];
     if (h->pinned[CTRL_NACTIVE] == 0) break;
   }
-  const int n_rtiles = h->pinned[CTRL_NRTILES];  // read back with the loop's exit flag
-  if (n_rtiles > 0) {
-    k_refine<<<dim3(n_rtiles, d.vn), 256, 0, st>>>(ws, d, fc);
-    ++launches;
-  }
-  k_solve<<<d.J, 32, 0, st>>>(ws, d, out_points, dbg);
-  ++launches;
   CUDA_TRY(cudaGetLastError());
   if (dbg.pix) CUDA_TRY(cudaMemcpyAsync(dbg.pix, ws.pix, (size_t)d.b * d.cap * 4, cudaMemcpyDeviceToDevice, st));
   if (dbg.stats) CUDA_TRY(cudaMemcpyAsync(dbg.stats, ws.stats, 4 * 8, cudaMemcpyDeviceToDevice, st));
@@ -440,9 +441,8 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
   k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
   k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
   k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
-  k_init_jobs<<<(d.J + 255) / 256, 256, 0, st>>>(ws, d);
   k_plan<<<1, 1024, 0, st>>>(ws, d, 0);
-  launches += 6;
+  launches += 5;
   if (ld.filter) {
     k_cc_init<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(lw, ld);
     k_cc_merge<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);

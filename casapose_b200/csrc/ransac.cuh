@@ -1,10 +1,10 @@
 // K2-K4 — the RANSAC loop of ransac_voting_batch
 // (/root/reference/casapose/pose_estimation/ransac_voting.py:310-368) for every (image, class) job.
 //
-//   k_init_jobs  loop state of every job (:310-316)
 //   k_hypgen     idxs -> hypotheses, exact float32 sequence (:319-322, :197-227), classifies each
 //                hypothesis for the filtered predicate and zeroes the vote counters
-//   k_plan       exclusive prefixes of scoring work items / refinement tiles over the jobs
+//   k_plan       loop state of every job (:310-316, round 0) and the exclusive prefixes of scoring work
+//                items / refinement tiles over the jobs
 //   k_score      THE HOT KERNEL: hypotheses x pixels inlier test (:230-249) and vote counts (:327)
 //   k_update     arg-max per keypoint (:328-333), best-so-far update (:336-338), stop test (:340-347)
 //   k_refine     re-vote of the winners and per-tile normal-equation sums (:349-362)
@@ -26,21 +26,6 @@ __device__ __forceinline__ float2 load_dir(const float2* __restrict__ vd, int t)
 
 __device__ __forceinline__ const float2* job_dirs(const WS& ws, const Dims& d, int img, int job, int tn, int v) {
   return ws.vdir + ((size_t)img * d.cap + ws.job_off[job]) * d.vn + (size_t)v * tn;
-}
-
-// ------------------------------------------------------------------------------------ init
-// one thread per job (round 0 only)
-__global__ void __launch_bounds__(256) k_init_jobs(WS ws, Dims d) {
-  const int job = blockIdx.x * 256 + threadIdx.x;
-  if (job >= d.J) return;
-  const int flags = ws.job_flags[job];
-  const bool act = !(flags & JOB_GATED) && ws.job_tn[job] > 0;
-  ws.job_flags[job] = act ? (flags | JOB_ACTIVE) : (flags & ~JOB_ACTIVE);
-  for (int v = 0; v < d.vn; ++v) {
-    ws.win_ratio[job * d.vn + v] = 0.f;  // :311-312
-    ws.win_pts[job * d.vn + v] = make_float2(0.f, 0.f);
-    ws.n_exact[job * d.vn + v] = 0;
-  }
 }
 
 // ------------------------------------------------------------------------------------ K2
@@ -107,7 +92,17 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
     const int job = s + tid;
     int ci = 0, cr = 0;
     if (job < d.J) {
-      const int flags = ws.job_flags[job], tn = ws.job_tn[job];
+      int flags = ws.job_flags[job];
+      const int tn = ws.job_tn[job];
+      if (rnd == 0) {  // loop state (:310-316)
+        flags = (!(flags & JOB_GATED) && tn > 0) ? (flags | JOB_ACTIVE) : (flags & ~JOB_ACTIVE);
+        ws.job_flags[job] = flags;
+        for (int v = 0; v < d.vn; ++v) {
+          ws.win_ratio[job * d.vn + v] = 0.f;
+          ws.win_pts[job * d.vn + v] = make_float2(0.f, 0.f);
+          ws.n_exact[job * d.vn + v] = 0;
+        }
+      }
       if (flags & JOB_ACTIVE) ci = ((tn + kChunk - 1) / kChunk) * d.vn;
       if (!(flags & JOB_GATED) && tn > 0) cr = (tn + kRefineTile - 1) / kRefineTile;
     }
@@ -491,12 +486,15 @@ __global__ void __launch_bounds__(512) k_update(WS ws, Dims d, int rnd, casa_ran
 }
 
 // ------------------------------------------------------------------------------------ K4
-// grid (n_rtiles, vn): one block per (1024-pixel tile of a job, keypoint); 4 pixels per thread.
+// grid (<= n_rtiles, vn), blocks stride over the (1024-pixel tile of a job, keypoint) pairs; 4 pixels per thread.
 // Re-votes the winner (:353) and accumulates the normal equations (:356-362): float32 products exactly
 // as the reference forms them (normal * inlier flag, so a non-finite direction poisons the sums as it
 // does there), float64 accumulation, fixed reduction order.
 __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc) {
-  const int rt = blockIdx.x, v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_rtiles = ws.rtile_start[d.J];
+  __shared__ double sred[8][5];
+  for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
   int lo = 0, hi = d.J;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -532,7 +530,6 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc) 
       }
     }
   }
-  __shared__ double sred[8][5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
 #pragma unroll
@@ -544,6 +541,8 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc) 
     double t = 0;
     for (int k = 0; k < 8; ++k) t += sred[k][tid];
     ws.partial[((size_t)rt * d.vn + v) * 5 + tid] = t;
+  }
+  __syncthreads();
   }
 }
 

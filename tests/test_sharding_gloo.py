@@ -45,6 +45,9 @@ def _worker(rank, world, port, n_images, out_dir):
     pts = sharding.sharded_vote(_oracle_vote, torch.from_numpy(d["mask"][s:e]), torch.from_numpy(d["vertex"][s:e]), 32,
                                 n_images=n_images, seed=3)
     np.save(os.path.join(out_dir, "rank%d.npy" % rank), pts.numpy())
+    pend = sharding.sharded_vote(_oracle_vote, torch.from_numpy(d["mask"][s:e]), torch.from_numpy(d["vertex"][s:e]), 32,
+                                 n_images=n_images, seed=3, async_gather=True)
+    assert torch.equal(pend.wait(), pts)
     dist.barrier()
     dist.destroy_process_group()
 

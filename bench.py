@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--variant", default="easy")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ransac", choices=["ransac", "ls"],
+                    help="ransac: BASELINE config 2 (the headline); ls: CoordLSVotingWeighted on config-1-shaped tensors")
     return ap.parse_args()
 
 
@@ -146,8 +148,69 @@ def run_reference(args):
     }))
 
 
+def run_ls(args):
+    """Secondary line: the weighted-LS keypoint layer (HBM-bound) on config-1-shaped
+    network outputs [b,480,640,9+18+9], filter_estimates=True, against the measured HBM copy bandwidth."""
+    import numpy as np
+    import torch
+
+    from casapose_b200 import _lib, synthetic
+    from casapose_b200.pose_estimation import CoordLSVotingWeighted
+    from oracle import ls_voting_np as OL
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device")
+    if _lib._sources_newer_than_lib():
+        _lib.build()
+    B = args.batch
+    d = synthetic.make_frames(B, H, W, synthetic.CONFIG_8_IDS, variant=args.variant, with_logits=True)
+    seg = torch.from_numpy(d["seg_logits"]).cuda()
+    direct = torch.from_numpy(d["vertex"].reshape(B, H, W, 18)).cuda()
+    conf = torch.from_numpy(d["conf_logits"]).cuda()
+    layer = CoordLSVotingWeighted("ls", OC + 1, num_points=VN, filter_estimates=True)
+    for _ in range(max(args.warmup, 3)):
+        layer([seg, direct, conf], check_finite=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        out = layer([seg, direct, conf], check_finite=False)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    alg_bytes = B * H * W * 4 * ((1 + OC) + 2 * VN + VN)  # SURVEY.md 8(d): 44.2 MB per frame at oc = 8
+    peak = None
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, measured)"
+    except Exception:
+        peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    t0 = time.perf_counter()
+    OL.coord_ls_voting_weighted(d["seg_logits"][:1], d["vertex"][:1].reshape(1, H, W, 18), d["conf_logits"][:1], filter_estimates=True)
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({
+        "metric": "weighted-LS keypoint layer frames/s (480x640, 8 obj x 9 kp, filter_estimates)", "value": B / (ms * 1e-3),
+        "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 elementwise, f64 accumulation",
+        "data": "synthetic", "config": {"workload": "config 1 shape: [b,480,640,9+18+9] network-output split -> CoordLSVotingWeighted(filter_estimates=True), batch %d" % B,
+                                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (alg_bytes / 1e6)},
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "CoordLSVotingWeighted (k_ls_classify .. k_ls_solve, 12 launches)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src},
+        "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": "numpy oracle, 1 frame, %.2f s" % cpu_s},
+        "gpu_launches": 12 * args.steps,
+    }))
+
+
 def main():
     args = parse()
+    if args.workload == "ls":
+        return run_ls(args)
     if args.impl == "reference":
         return run_reference(args)
 

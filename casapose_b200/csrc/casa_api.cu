@@ -410,7 +410,8 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
   const size_t npx = (size_t)d.b * d.hw;
   size_t cur = L.total;
   const size_t off_cls9 = bump(cur, npx), off_parent = bump(cur, npx * 4), off_count = bump(cur, npx * 4),
-               off_roots = bump(cur, npx * 4), off_nroots = bump(cur, (size_t)d.b * 4), off_sel = bump(cur, (size_t)d.J * 4);
+               off_roots = bump(cur, npx * 4), off_nroots = bump(cur, (size_t)d.b * 4), off_sel = bump(cur, (size_t)d.J * 4),
+               off_wt = bump(cur, (size_t)d.b * d.cap * 4), off_cconf = bump(cur, (size_t)d.b * d.cap * d.vn * 4);
   rc = ensure(&h->ws_mem, &h->ws_bytes, cur);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -423,6 +424,8 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
   lw.roots = (int*)(base + off_roots);
   lw.nroots = (int*)(base + off_nroots);
   lw.sel = (int*)(base + off_sel);
+  lw.wt = (float*)(base + off_wt);
+  lw.cconf = (float*)(base + off_cconf);
   LsDims ld;
   ld.b = d.b; ld.h = d.h; ld.w = d.w; ld.nc = p->num_classes; ld.oc = d.oc; ld.vn = d.vn; ld.hw = d.hw;
   ld.sigmoid_weights = p->sigmoid_weights ? 1 : 0;
@@ -437,21 +440,34 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
 
   CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
-  k_ls_classify<<<dim3(d.nct, d.b), 256, 0, st>>>(seg, ws, d, lw, ld);
+  {
+    const size_t sm = (size_t)kCountTile * ld.nc * 4;
+    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_ls_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_ls_classify<<<dim3(d.nct, d.b), 256, sm, st>>>(seg, ws, d, lw, ld);
+  }
   k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
   k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
   k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
   k_plan<<<1, 1024, 0, st>>>(ws, d, 0);
   launches += 5;
   if (ld.filter) {
-    k_cc_init<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(lw, ld);
+    k_cc_init<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
     k_cc_merge<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
     k_cc_flatten<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
     k_cc_select<<<d.J, 256, 0, st>>>(lw, ld);
     launches += 4;
   }
   const int grid_x = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
-  k_ls_reduce<<<dim3(grid_x, d.vn), 256, 0, st>>>(ws, d, lw, ld, seg, direct, conf);
+  {
+    const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
+    if (d.vn == 9)
+      k_gather_dirs<18><<<dim3(gx, d.J), 256, 0, st>>>(direct, ws, d);
+    else
+      k_gather_dirs<0><<<dim3(gx, d.J), 256, 0, st>>>(direct, ws, d);
+    k_ls_weights<<<dim3(gx, d.J), 256, 0, st>>>(ws, d, lw, ld, seg, conf);
+    launches += 2;
+  }
+  k_ls_reduce<<<dim3(grid_x, d.vn), 256, 0, st>>>(ws, d, lw, ld);
   k_ls_solve<<<d.J, 32, 0, st>>>(ws, d, ld, out_points, dbg.sums);
   launches += 2;
   CUDA_TRY(cudaGetLastError());

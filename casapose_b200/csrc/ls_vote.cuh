@@ -32,6 +32,8 @@ struct LsWS {
   int* roots;           // [b*hw]  list of root pixels per image
   int* nroots;          // [b]
   int* sel;             // [J]     selected component: root pixel, -1 = none, -2 = label 0 (background)
+  float* wt;            // [b*cap] weight hot * component mask of every listed pixel (job list order)
+  float* cconf;         // [b*cap*vn] softplus / sigmoid confidence weights, keypoint-major per job like WS::vdir
 };
 
 // softmax(seg * 1e6) in float32 (:38-41): z = x * 1e6; e = exp(z - max z); e / sum e
@@ -61,27 +63,85 @@ __device__ __forceinline__ float hard_softmax_one(const float* __restrict__ row,
   return __fdiv_rn(e, s);
 }
 
-// same tiling and outputs as k_mask_bits (compaction.cuh), fed by the segmentation logits
+// hot value of class `cls` from a staged row.  Fast path: when the runner-up is more than 110 below the
+// maximum (in units of 1e6 * logit) every other exp() is exactly 0 in float32, the sum is exactly 1 and the
+// softmax is exactly one-hot — true for all but near-tie pixels.
+__device__ __forceinline__ float hot_of_row(const float* row, int nc, int cls) {
+  float m = -3.4e38f, m2 = -3.4e38f;
+  int arg = 0;
+  for (int c = 0; c < nc; ++c) {
+    const float z = __fmul_rn(row[c], 1.0e6f);
+    if (z > m) {
+      m2 = m;
+      m = z;
+      arg = c;
+    } else if (z > m2) {
+      m2 = z;
+    }
+  }
+  if (m - m2 > 110.f) return arg == cls ? 1.0f : 0.0f;
+  float sum = 0.f, e = 0.f;
+  for (int c = 0; c < nc; ++c) {
+    const float t = expf(__fsub_rn(__fmul_rn(row[c], 1.0e6f), m));
+    sum = __fadd_rn(sum, t);
+    if (c == cls) e = t;
+  }
+  return __fdiv_rn(e, sum);
+}
+
+// same tiling and outputs as k_mask_bits (compaction.cuh), fed by the segmentation logits: the tile's
+// [1024 x nc] floats are staged in shared memory with coalesced loads, then every thread classifies 4 pixels
+extern __shared__ float ls_smem[];
 __global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ seg, WS ws, Dims d, LsWS lw, LsDims ld) {
   const int img = blockIdx.y, tile = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   __shared__ int scnt[32];
   if (tid < 32) scnt[tid] = 0;
+  const int p0 = tile * kCountTile;
+  const int npx = min(kCountTile, d.hw - p0);
+  const float* slab = seg + ((size_t)img * d.hw + p0) * ld.nc;
+  const int nfl = npx * ld.nc;
+  for (int i = tid; i < nfl; i += 256) ls_smem[i] = __ldg(slab + i);
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int p = tile * kCountTile + k * 256 + tid;
+    const int q = k * 256 + tid;
     uint32_t m = 0;
-    if (p < d.hw) {
-      float hot[33];
-      hard_softmax(seg + ((size_t)img * d.hw + p) * ld.nc, ld.nc, hot);
-      int c9 = 0;
-      for (int c = 1; c < ld.nc; ++c) {
-        m |= (uint32_t)(hot[c] != 0.f) << (c - 1);
-        if ((int)__fadd_rn(hot[c], 0.1f) == 1) c9 = c;  // :44 (at most one class can reach 0.9)
+    if (q < npx) {
+      const float* row = ls_smem + q * ld.nc;
+      float mx = -3.4e38f, m2 = -3.4e38f;
+      int arg = 0;
+      for (int c = 0; c < ld.nc; ++c) {
+        const float z = __fmul_rn(row[c], 1.0e6f);
+        if (z > mx) {
+          m2 = mx;
+          mx = z;
+          arg = c;
+        } else if (z > m2) {
+          m2 = z;
+        }
       }
-      ws.bits[(size_t)img * d.hw + p] = m;
-      lw.cls9[(size_t)img * d.hw + p] = (unsigned char)c9;
+      int c9 = 0;
+      if (mx - m2 > 110.f) {  // exactly one-hot
+        if (arg > 0) {
+          m = 1u << (arg - 1);
+          c9 = arg;
+        }
+      } else {
+        float hot[33];
+        float sum = 0.f;
+        for (int c = 0; c < ld.nc; ++c) {
+          hot[c] = expf(__fsub_rn(__fmul_rn(row[c], 1.0e6f), mx));
+          sum = __fadd_rn(sum, hot[c]);
+        }
+        for (int c = 1; c < ld.nc; ++c) {
+          const float hv = __fdiv_rn(hot[c], sum);
+          m |= (uint32_t)(hv != 0.f) << (c - 1);
+          if ((int)__fadd_rn(hv, 0.1f) == 1) c9 = c;  // :44 (at most one class can reach 0.9)
+        }
+      }
+      ws.bits[(size_t)img * d.hw + p0 + q] = m;
+      lw.cls9[(size_t)img * d.hw + p0 + q] = (unsigned char)c9;
     }
     for (int c = 0; c < d.oc; ++c) {
       const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
@@ -93,13 +153,21 @@ __global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ s
 }
 
 // ---------------------------------------------------------------------------------- connected components
-__device__ __forceinline__ int uf_find(const int* parent, int x) {
-  int p = parent[x];
-  while (p != x) {
-    x = p;
-    p = parent[x];
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+  int r = x;
+  while (true) {
+    const int p = parent[r];
+    if (p == r) break;
+    r = p;
   }
-  return x;
+  // path compression (racy but monotone: parent[i] <= i always and parents only ever decrease, so the walk
+  // strictly descends and must stop at or below r even if other threads re-rooted the chain meanwhile)
+  while (x > r) {
+    const int p = parent[x];
+    if (p > r) parent[x] = r;
+    x = p;
+  }
+  return r;
 }
 
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
@@ -118,14 +186,27 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
+// Every pixel starts under the first pixel of its horizontal same-class run inside its warp's 32-pixel
+// segment (runs are pre-merged with ballots, no atomics); count and root list are reset.
 __global__ void __launch_bounds__(256) k_cc_init(LsWS lw, LsDims ld) {
-  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= (size_t)ld.b * ld.hw) return;
-  lw.parent[i] = (int)(i % ld.hw);
-  lw.count[i] = 0;
-  if (i < (size_t)ld.b) lw.nroots[i] = 0;
+  const int img = blockIdx.y;
+  const int p = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
+  const unsigned char* cls = lw.cls9 + (size_t)img * ld.hw;
+  const int c = p < ld.hw ? cls[p] : 0;
+  const int x = p % ld.w;
+  const int cl = __shfl_up_sync(0xffffffffu, c, 1);
+  const bool start = lane == 0 || x == 0 || cl != c;  // a run starts here
+  const unsigned sb = __ballot_sync(0xffffffffu, start);
+  if (p < ld.hw) {
+    const int sl = 31 - __clz(sb & (0xffffffffu >> (31 - lane)));  // nearest run start at or below this lane
+    lw.parent[(size_t)img * ld.hw + p] = p - (lane - sl);
+    lw.count[(size_t)img * ld.hw + p] = 0;
+  }
+  if (p == 0) lw.nroots[img] = 0;
 }
 
+// Unions only where they are not implied: the 32-pixel segment boundary, and the FIRST pixel of every
+// horizontal overlap with the row above (left and upper-left neighbours both of the class => implied).
 __global__ void __launch_bounds__(256) k_cc_merge(LsWS lw, LsDims ld) {
   const int img = blockIdx.y;
   const int p = blockIdx.x * 256 + threadIdx.x;
@@ -135,20 +216,28 @@ __global__ void __launch_bounds__(256) k_cc_merge(LsWS lw, LsDims ld) {
   const int c = cls[p];
   if (c == 0) return;
   const int y = p / ld.w, x = p - y * ld.w;
-  if (x > 0 && cls[p - 1] == c) uf_union(parent, p, p - 1);
-  if (y > 0 && cls[p - ld.w] == c) uf_union(parent, p, p - ld.w);
+  const bool left = x > 0 && cls[p - 1] == c;
+  if (left && (threadIdx.x & 31) == 0) uf_union(parent, p, p - 1);
+  if (y > 0 && cls[p - ld.w] == c) {
+    const bool upleft = x > 0 && cls[p - ld.w - 1] == c;
+    if (!(left && upleft)) uf_union(parent, p, p - ld.w);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_cc_flatten(LsWS lw, LsDims ld) {
   const int img = blockIdx.y;
-  const int p = blockIdx.x * 256 + threadIdx.x;
-  if (p >= ld.hw) return;
-  if (lw.cls9[(size_t)img * ld.hw + p] == 0) return;
-  int* parent = lw.parent + (size_t)img * ld.hw;
-  const int r = uf_find(parent, p);
-  parent[p] = r;
-  atomicAdd(&lw.count[(size_t)img * ld.hw + r], 1);
-  if (r == p) lw.roots[(size_t)img * ld.hw + atomicAdd(&lw.nroots[img], 1)] = p;
+  const int p = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
+  const bool fg = p < ld.hw && lw.cls9[(size_t)img * ld.hw + p] != 0;
+  int r = -1;
+  if (fg) {
+    int* parent = lw.parent + (size_t)img * ld.hw;
+    r = uf_find(parent, p);
+    parent[p] = r;
+    if (r == p) lw.roots[(size_t)img * ld.hw + atomicAdd(&lw.nroots[img], 1)] = p;
+  }
+  // component sizes: one atomic per distinct root in the warp (neighbouring pixels share their root)
+  const unsigned same = __match_any_sync(0xffffffffu, r);
+  if (fg && lane == __ffs(same) - 1) atomicAdd(&lw.count[(size_t)img * ld.hw + r], __popc(same));
 }
 
 // one block per (image, class): bincount -> threshold -> top_k -> pick index `which` (:64-76).
@@ -226,9 +315,39 @@ __device__ __forceinline__ float ls_weight(float x, int sigmoid_weights) {
   return x > thr ? x : (x < -thr ? ex : logf(__fadd_rn(ex, 1.0f)));
 }
 
-// persistent over the refinement tiles: blockIdx.x strides over tiles, blockIdx.y = keypoint
-__global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDims ld, const float* __restrict__ seg,
-                                                   const float* __restrict__ direct, const float* __restrict__ conf) {
+// One thread per listed pixel of a job: weight = hot_seg * component mask (:39-41, :72-79), and the pixel's
+// confidence row turned into softplus / sigmoid weights (:32-35), stored keypoint-major like the directions.
+__global__ void __launch_bounds__(256) k_ls_weights(WS ws, Dims d, LsWS lw, LsDims ld, const float* __restrict__ seg,
+                                                    const float* __restrict__ conf) {
+  const int job = blockIdx.y, img = job / d.oc, c = job - img * d.oc;
+  const int tn = ws.job_tn[job];
+  if (tn <= 0) return;
+  const int off = ws.job_off[job];
+  const uint32_t* pix = ws.pix + (size_t)img * d.cap + off;
+  const int sel = ld.filter ? lw.sel[job] : 0;
+  float* wt = lw.wt + (size_t)img * d.cap + off;
+  float* cc = lw.cconf + ((size_t)img * d.cap + off) * d.vn;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < tn; t += gridDim.x * 256) {
+    const uint32_t pk = pix[t];
+    const int x = pk & 0xFFFFu, y = pk >> 16;
+    const size_t p = (size_t)img * ld.hw + (size_t)y * ld.w + x;
+    float row[33];
+    for (int k = 0; k < ld.nc; ++k) row[k] = __ldg(seg + p * ld.nc + k);
+    float w = hot_of_row(row, ld.nc, c + 1);  // hot_seg (:39-41)
+    if (ld.filter) {                          // copy_components * hot_seg (:72-79)
+      const int c9 = lw.cls9[p];
+      const bool keep = sel == -2 ? (c9 != c + 1) : (sel >= 0 && c9 == c + 1 && lw.parent[p] == sel);
+      w = __fmul_rn(keep ? 1.0f : 0.0f, w);
+    }
+    wt[t] = w;
+    if (w != 0.f)
+      for (int v = 0; v < d.vn; ++v) cc[(size_t)v * tn + t] = ls_weight(__ldg(conf + p * ld.vn + v), ld.sigmoid_weights);
+  }
+}
+
+// persistent over the refinement tiles: blockIdx.x strides over tiles, blockIdx.y = keypoint.  All operands
+// come from the compact per-job arrays (pix, wt, vdir, cconf): coalesced, each read once.
+__global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDims ld) {
   const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_rtiles = ws.rtile_start[d.J];
   __shared__ double sred[8][5];
@@ -241,29 +360,26 @@ __global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDim
     }
     const int job = lo, tile = rt - ws.rtile_start[job];
     const int tn = ws.job_tn[job];
-    const int img = job / d.oc, c = job - img * d.oc;
-    const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
-    const int sel = ld.filter ? lw.sel[job] : 0;
+    const int img = job / d.oc;
+    const size_t base = (size_t)img * d.cap + ws.job_off[job];
+    const uint32_t* pix = ws.pix + base;
+    const float* wt = lw.wt + base;
+    const float2* vd = ws.vdir + base * d.vn + (size_t)v * tn;
+    const float* cc = lw.cconf + base * d.vn + (size_t)v * tn;
     double s[5] = {0, 0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < kRefineTile / 256; ++k) {
       const int t = tile * kRefineTile + k * 256 + tid;
       if (t >= tn) continue;
+      const float w = wt[t];
+      if (w == 0.f) continue;  // multiply_no_nan (:107-108)
       const uint32_t pk = pix[t];
       const int x = pk & 0xFFFFu, y = pk >> 16;
-      const size_t p = (size_t)img * ld.hw + (size_t)y * ld.w + x;
-      float wt = hard_softmax_one(seg + p * ld.nc, ld.nc, c + 1);  // hot_seg (:39-41)
-      if (ld.filter) {  // copy_components * hot_seg (:72-79)
-        const int c9 = lw.cls9[p];
-        const bool keep = sel == -2 ? (c9 != c + 1) : (sel >= 0 && c9 == c + 1 && lw.parent[p] == sel);
-        wt = __fmul_rn(keep ? 1.0f : 0.0f, wt);
-      }
-      if (wt == 0.f) continue;  // multiply_no_nan (:107-108)
-      const float2 dv = __ldg(reinterpret_cast<const float2*>(direct + (p * ld.vn + v) * 2));  // (n0, n1) = (dy, dx)
+      const float2 dv = __ldg(vd + t);  // (n0, n1) = (dy, dx)
       const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dv.x, dv.x), __fmul_rn(dv.y, dv.y)));  // :89
       const float n0 = nrm != 0.f ? __fdiv_rn(dv.x, nrm) : 0.f;  // divide_no_nan :90
       const float n1 = nrm != 0.f ? __fdiv_rn(dv.y, nrm) : 0.f;
-      const float wc = ls_weight(__ldg(conf + p * ld.vn + v), ld.sigmoid_weights);
+      const float wc = cc[t];
       const float r00 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n0, n0)), wc);  // :92-94
       const float r01 = __fmul_rn(__fsub_rn(0.0f, __fmul_rn(n0, n1)), wc);
       const float r11 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n1, n1)), wc);
@@ -271,11 +387,11 @@ __global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDim
       const float cx = __fdiv_rn(__fadd_rn((float)x, 0.5f), fh);  // :96
       const float q0 = __fadd_rn(__fmul_rn(r00, cy), __fmul_rn(r01, cx));  // :103-105
       const float q1 = __fadd_rn(__fmul_rn(r01, cy), __fmul_rn(r11, cx));
-      s[0] += (double)__fmul_rn(r00, wt);  // :108, :113
-      s[1] += (double)__fmul_rn(r01, wt);
-      s[2] += (double)__fmul_rn(r11, wt);
-      s[3] += (double)__fmul_rn(q0, wt);   // :107, :114
-      s[4] += (double)__fmul_rn(q1, wt);
+      s[0] += (double)__fmul_rn(r00, w);  // :108, :113
+      s[1] += (double)__fmul_rn(r01, w);
+      s[2] += (double)__fmul_rn(r11, w);
+      s[3] += (double)__fmul_rn(q0, w);   // :107, :114
+      s[4] += (double)__fmul_rn(q1, w);
     }
 #pragma unroll
     for (int k = 0; k < 5; ++k) {

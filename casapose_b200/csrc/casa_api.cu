@@ -39,7 +39,8 @@ struct casa_handle {
   void* io_mem = nullptr;  // device staging of the host-buffer entry points
   size_t io_bytes = 0;
   int* pinned = nullptr;   // CTRL_WORDS ints, page-locked
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t part_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_round = nullptr;
   uint32_t last_status = 0;
   int64_t last_launches = 0;
@@ -70,6 +71,8 @@ extern "C" int casa_create(int device, casa_handle** out) {
   CUDA_TRY(cudaHostAlloc((void**)&h->pinned, CTRL_WORDS * sizeof(int), cudaHostAllocDefault));
   CUDA_TRY(cudaHostAlloc((void**)&h->pinned_stats, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->part_ev[i], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_round, cudaEventDisableTiming));
@@ -87,6 +90,9 @@ extern "C" int casa_destroy(casa_handle* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->pinned_stats) cudaFreeHost(h->pinned_stats);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 8; ++i)
+    if (h->part_ev[i]) cudaEventDestroy(h->part_ev[i]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_round) cudaEventDestroy(h->ev_round);
@@ -365,26 +371,63 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   const size_t mask_n = (size_t)p->b * hw * p->oc * 4, vert_n = (size_t)p->b * hw * vfields * p->vn * 2 * 4;
   const size_t out_b = (size_t)p->b * p->oc * p->vn * 2 * 4;
   cudaStream_t st = h->own_stream;
-  // Pinned (page-locked) host buffers are read by the kernels directly: the mask is streamed once by
-  // k_mask_bits and only the masked pixels' rows of the vector field are fetched by k_gather_dirs, so
-  // about 200 MB instead of 511 MB cross PCIe for a 16-frame batch.  Pageable buffers are staged.
+  // Pinned (page-locked) host buffers: the mask is DMA-copied in up to 4 image ranges on a copy stream while the
+  // previous range is being voted on, and the vector field is never copied — k_gather_dirs reads only the masked
+  // pixels' rows straight from the mapped host buffer.  About 200 MB instead of 511 MB cross PCIe for a 16-frame
+  // batch, and the voting hides behind the mask transfer.  Pageable buffers are staged in one piece.
   const void *dm = nullptr, *dv = nullptr;
   const bool zero_copy = !getenv("CASA_NO_ZERO_COPY") && host_pointer_is_mapped(mask_host, &dm) && host_pointer_is_mapped(vertex_host, &dv);
-  const size_t mask_b = zero_copy ? 0 : (mask_n + 255) & ~size_t(255);
+  const size_t mask_b = (mask_n + 255) & ~size_t(255);
   const size_t vert_b = zero_copy ? 0 : (vert_n + 255) & ~size_t(255);
   rc = ensure(&h->io_mem, &h->io_bytes, mask_b + vert_b + out_b);
   if (rc) return rc;
-  const float* dmask = (const float*)dm;
-  const float* dvert = (const float*)dv;
+  float* dmask = (float*)h->io_mem;
   float* dout = (float*)((char*)h->io_mem + mask_b + vert_b);
   if (!zero_copy) {
-    CUDA_TRY(cudaMemcpyAsync(h->io_mem, mask_host, mask_n, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync((char*)h->io_mem + mask_b, vertex_host, vert_n, cudaMemcpyHostToDevice, st));
-    dmask = (const float*)h->io_mem;
-    dvert = (const float*)((char*)h->io_mem + mask_b);
+    float* dvert = (float*)((char*)h->io_mem + mask_b);
+    CUDA_TRY(cudaMemcpyAsync(dmask, mask_host, mask_n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dvert, vertex_host, vert_n, cudaMemcpyHostToDevice, st));
+    rc = casa_ransac_vote(h, p, dmask, dvert, nullptr, nullptr, dout, nullptr, (void*)st);
+    if (rc) return rc;
+  } else {
+    int parts = p->b >= 8 ? 4 : (p->b >= 2 ? 2 : 1);
+    if (getenv("CASA_HOST_PARTS")) parts = atoi(getenv("CASA_HOST_PARTS"));
+    if (parts < 1) parts = 1;
+    if (parts > 8) parts = 8;
+    if (parts > p->b) parts = p->b;
+    const size_t mask_img = hw * p->oc, vert_img = hw * vfields * p->vn * 2, out_img = (size_t)p->oc * p->vn * 2;
+    int start[9];
+    for (int k = 0; k <= parts; ++k) start[k] = (int)((long long)p->b * k / parts);
+    for (int k = 0; k < parts; ++k) {  // all mask copies are queued up front on the copy stream
+      const size_t o = (size_t)start[k] * mask_img, n = (size_t)(start[k + 1] - start[k]) * mask_img;
+      CUDA_TRY(cudaMemcpyAsync(dmask + o, mask_host + o, n * 4, cudaMemcpyHostToDevice, h->copy_stream));
+      CUDA_TRY(cudaEventRecord(h->part_ev[k], h->copy_stream));
+    }
+    int64_t launches = 0;
+    double score_ms = 0.0;
+    int64_t score_launches = 0;
+    uint64_t stats[4] = {0, 0, 0, 0};
+    uint32_t status = 0;
+    for (int k = 0; k < parts; ++k) {
+      casa_ransac_params pp = *p;
+      pp.b = start[k + 1] - start[k];
+      pp.image_offset = p->image_offset + start[k];
+      CUDA_TRY(cudaStreamWaitEvent(st, h->part_ev[k], 0));
+      rc = casa_ransac_vote(h, &pp, dmask + (size_t)start[k] * mask_img, (const float*)dv + (size_t)start[k] * vert_img,
+                            nullptr, nullptr, dout + (size_t)start[k] * out_img, nullptr, (void*)st);
+      if (rc) return rc;
+      launches += h->last_launches;
+      score_ms += h->score_ms;
+      score_launches += h->score_launches;
+      status |= h->last_status;
+      for (int j = 0; j < 4; ++j) stats[j] += h->stats[j];
+    }
+    h->last_launches = launches;
+    h->score_ms = score_ms;
+    h->score_launches = score_launches;
+    h->last_status = status;
+    for (int j = 0; j < 4; ++j) h->stats[j] = stats[j];
   }
-  rc = casa_ransac_vote(h, p, dmask, dvert, nullptr, nullptr, dout, nullptr, (void*)st);
-  if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return CASA_OK;

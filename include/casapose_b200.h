@@ -131,9 +131,11 @@ int casa_ransac_vote_seg(casa_handle* h, const casa_ransac_params* p, const floa
                          float* out_points, const casa_ransac_debug* debug, void* stream);
 
 /*
- * Same call with HOST buffers: copies mask/vertex host->device (pipelined per image),
- * runs the path and copies out_points back; returns after the result is on the host.
- * Host buffers may be pageable or pinned (pinned is faster).
+ * Same call with HOST buffers; returns after out_points is on the host.
+ * Pinned (page-locked, device-mapped) buffers take the fast path: the mask is DMA-copied in up to 4 image
+ * ranges on a copy stream while the previous range is voted on, and the vector field is NOT copied — the
+ * gather kernel reads only the masked pixels' rows from the mapped host buffer (about 200 MB instead of
+ * 511 MB over PCIe for sixteen 480x640 frames).  Pageable buffers are staged in one piece.
  */
 int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
                           const float* vertex_host, float* out_points_host);

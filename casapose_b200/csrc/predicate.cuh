@@ -144,7 +144,7 @@ inline FilterConsts filter_consts(float inlier_thresh, int force_exact) {
   const double dC = 1.05 * (u + 8.0 * u * thr);
   const double d_ref = dC / s0;   // angular half-width from the reference's own rounding
   const double d_fil = 8.0 * u;   // angular error of the filter's two linear forms (< 3.5 u)
-  const double delta = 1.5 * (d_ref + d_fil);
+  const double delta = 1.2 * (d_ref + d_fil);  // both terms are worst-case first-order bounds; 20 % covers second order
   if (!(theta0 - delta > 1e-3)) return f;
   // verify the band really covers dC on both sides (curvature of cos)
   if (!(cos(theta0 - delta) >= thr + dC && cos(theta0 + delta) <= thr - dC)) return f;

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "compaction.cuh"
 #include "ls_vote.cuh"
@@ -49,7 +51,17 @@ struct casa_handle {
   int64_t score_launches = 0;
   uint64_t stats[4] = {0, 0, 0, 0};
   unsigned long long* pinned_stats = nullptr;  // 4 words, page-locked
+  int score_occ = 0;
+  int use_graph = 1;
+  std::vector<struct casa_graph*> graphs;
   int score_p = 3;  // min resident blocks/SM the scoring kernel is compiled for (3: 80 regs, 4: 64 regs)
+};
+
+struct casa_graph {
+  uint64_t key = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<cudaGraphNode_t> knodes;  // kernel nodes in list order
 };
 
 extern "C" int casa_version(void) { return CASA_VERSION; }
@@ -76,6 +88,7 @@ extern "C" int casa_create(int device, casa_handle** out) {
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_round, cudaEventDisableTiming));
+  if (getenv("CASA_NO_GRAPH")) h->use_graph = 0;
   const char* sp = getenv("CASA_SCORE_MINB");
   if (sp && atoi(sp) == 4) h->score_p = 4;
   *out = h;
@@ -85,6 +98,11 @@ extern "C" int casa_create(int device, casa_handle** out) {
 extern "C" int casa_destroy(casa_handle* h) {
   if (!h) return CASA_OK;
   cudaSetDevice(h->device);
+  for (casa_graph* g : h->graphs) {
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+  }
   if (h->ws_mem) cudaFree(h->ws_mem);
   if (h->io_mem) cudaFree(h->io_mem);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -218,16 +236,6 @@ int ensure(void** mem, size_t* have, size_t need) {
   return CASA_OK;
 }
 
-template <int MINB>
-int launch_score(casa_handle* h, const ScoreArgs& a, cudaStream_t st) {
-  static thread_local int occ = 0;
-  if (occ == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score<MINB>, kScoreThreads, 0));
-  if (occ < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
-  k_score<MINB><<<h->sm_count * occ, kScoreThreads, 0, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
-  return CASA_OK;
-}
-
 }  // namespace
 
 extern "C" size_t casa_ransac_workspace_bytes(const casa_ransac_params* p) {
@@ -237,6 +245,154 @@ extern "C" size_t casa_ransac_workspace_bytes(const casa_ransac_params* p) {
 }
 
 // ------------------------------------------------------------------------------------------------ ransac vote
+
+// ---- launch lists: the kernel sequence of a round is described once and either launched directly or replayed
+// ---- as a CUDA graph whose kernel-node parameters are patched per call (CUDA graphs instead of launch gaps).
+namespace {
+
+enum StepKind { STEP_KERNEL, STEP_EV0, STEP_EV1, STEP_READBACK };
+
+struct Step {
+  StepKind kind = STEP_KERNEL;
+  const void* func = nullptr;
+  dim3 grid, block;
+  size_t smem = 0;
+  alignas(16) char buf[704];
+  size_t off[8];
+  size_t used = 0;
+  int n = 0;
+  template <class T>
+  Step& arg(const T& v) {
+    used = (used + alignof(T) - 1) & ~(alignof(T) - 1);
+    memcpy(buf + used, &v, sizeof(T));
+    off[n++] = used;
+    used += sizeof(T);
+    return *this;
+  }
+  void ptrs(void** out) {
+    for (int i = 0; i < n; ++i) out[i] = buf + off[i];
+  }
+};
+
+Step kstep(const void* func, dim3 grid, dim3 block, size_t smem = 0) {
+  Step s;
+  s.func = func;
+  s.grid = grid;
+  s.block = block;
+  s.smem = smem;
+  return s;
+}
+
+Step special(StepKind k) {
+  Step s;
+  s.kind = k;
+  return s;
+}
+
+uint64_t fnv(uint64_t hsh, const void* p, size_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) hsh = (hsh ^ b[i]) * 1099511628211ull;
+  return hsh;
+}
+
+}  // namespace
+
+
+static int run_direct(casa_handle* h, std::vector<Step>& steps, const WS& ws, cudaStream_t st) {
+  for (Step& s : steps) {
+    switch (s.kind) {
+      case STEP_KERNEL: {
+        void* args[8];
+        s.ptrs(args);
+        CUDA_TRY(cudaLaunchKernel(s.func, s.grid, s.block, args, s.smem, st));
+        break;
+      }
+      case STEP_EV0: CUDA_TRY(cudaEventRecord(h->ev0, st)); break;
+      case STEP_EV1: CUDA_TRY(cudaEventRecord(h->ev1, st)); break;
+      case STEP_READBACK:
+        // the reference's data-dependent `while` (:318): one 32-byte read-back per round
+        CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->pinned_stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(h->ev_round, st));
+        break;
+    }
+  }
+  return CASA_OK;
+}
+
+static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cudaStream_t st) {
+  uint64_t key = 1469598103934665603ull;
+  for (const Step& s : steps) {
+    key = fnv(key, &s.kind, sizeof(s.kind));
+    key = fnv(key, &s.func, sizeof(s.func));
+    key = fnv(key, &s.grid, sizeof(s.grid));
+    key = fnv(key, &s.block, sizeof(s.block));
+    key = fnv(key, &s.smem, sizeof(s.smem));
+  }
+  key = fnv(key, &ws.ctrl, sizeof(ws.ctrl));  // the read-back nodes carry workspace addresses
+  casa_graph* g = nullptr;
+  for (casa_graph* c : h->graphs)
+    if (c->key == key) g = c;
+  if (!g) {
+    g = new casa_graph();
+    g->key = key;
+    CUDA_TRY(cudaGraphCreate(&g->graph, 0));
+    cudaGraphNode_t prev = nullptr;
+    auto deps = [&]() { return prev ? &prev : nullptr; };
+    for (Step& s : steps) {
+      cudaGraphNode_t node = nullptr;
+      const size_t nd = prev ? 1 : 0;
+      if (s.kind == STEP_KERNEL) {
+        void* args[8];
+        s.ptrs(args);
+        cudaKernelNodeParams kp;
+        memset(&kp, 0, sizeof(kp));
+        kp.func = (void*)s.func;
+        kp.gridDim = s.grid;
+        kp.blockDim = s.block;
+        kp.sharedMemBytes = (unsigned)s.smem;
+        kp.kernelParams = args;
+        CUDA_TRY(cudaGraphAddKernelNode(&node, g->graph, deps(), nd, &kp));
+        g->knodes.push_back(node);
+      } else if (s.kind == STEP_EV0 || s.kind == STEP_EV1) {
+        CUDA_TRY(cudaGraphAddEventRecordNode(&node, g->graph, deps(), nd, s.kind == STEP_EV0 ? h->ev0 : h->ev1));
+      } else {
+        CUDA_TRY(cudaGraphAddMemcpyNode1D(&node, g->graph, deps(), nd, h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost));
+        prev = node;
+        CUDA_TRY(cudaGraphAddMemcpyNode1D(&node, g->graph, &prev, 1, h->pinned_stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        prev = node;
+        CUDA_TRY(cudaGraphAddEventRecordNode(&node, g->graph, &prev, 1, h->ev_round));
+      }
+      prev = node;
+    }
+    CUDA_TRY(cudaGraphInstantiate(&g->exec, g->graph, 0));
+    if (h->graphs.size() >= 16) {  // tiny cache: drop the oldest shape
+      casa_graph* old = h->graphs.front();
+      cudaGraphExecDestroy(old->exec);
+      cudaGraphDestroy(old->graph);
+      delete old;
+      h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back(g);
+  } else {
+    size_t k = 0;
+    for (Step& s : steps) {
+      if (s.kind != STEP_KERNEL) continue;
+      void* args[8];
+      s.ptrs(args);
+      cudaKernelNodeParams kp;
+      memset(&kp, 0, sizeof(kp));
+      kp.func = (void*)s.func;
+      kp.gridDim = s.grid;
+      kp.blockDim = s.block;
+      kp.sharedMemBytes = (unsigned)s.smem;
+      kp.kernelParams = args;
+      CUDA_TRY(cudaGraphExecKernelNodeSetParams(g->exec, g->knodes[k++], &kp));
+    }
+  }
+  CUDA_TRY(cudaGraphLaunch(g->exec, st));
+  return CASA_OK;
+}
 
 static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const float* mask, int mask_is_seg,
                             const float* vertex, const int32_t* idxs, const float* selection, float* out_points,
@@ -263,56 +419,51 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   h->score_ms = 0.0;
   h->score_launches = 0;
 
-  const int vec4 = ((((size_t)d.hw * d.oc) & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
-  if (mask_is_seg)
-    k_seg_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d);
-  else
-    k_mask_bits<<<dim3(d.nct, d.b), 256, 0, st>>>(mask, ws, d, vec4);
-  k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
-  k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
-  k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
-  launches += 4;
-  if ((float)d.hw > p->max_num) {
-    k_cap_filter<<<d.J, 1024, 0, st>>>(ws, d, selection);
-    ++launches;
-  }
-  {
-    const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
-    if (d.vn == 9)
-      k_gather_dirs<18><<<dim3(gx, d.J), 256, 0, st>>>(vertex, ws, d);
-    else
-      k_gather_dirs<0><<<dim3(gx, d.J), 256, 0, st>>>(vertex, ws, d);
-    ++launches;
-  }
-  CUDA_TRY(cudaGetLastError());
-
   ScoreArgs sa;
   sa.ws = ws;
   sa.d = d;
   sa.fc = fc;
-  const int upd_threads = 32 * d.vn;
+  if (h->score_occ == 0) {
+    if (h->score_p == 4)
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<4>, kScoreThreads, 0));
+    else
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<3>, kScoreThreads, 0));
+    if (h->score_occ < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
+  }
+  const void* score_fn = h->score_p == 4 ? (const void*)k_score<4> : (const void*)k_score<3>;
   const int refine_gx = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
+  const int gather_gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
+  const int vec4 = ((((size_t)d.hw * d.oc) & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
+
   for (int rnd = 0; rnd < d.max_iter; ++rnd) {
-    k_plan<<<1, 1024, 0, st>>>(ws, d, rnd);
-    k_hypgen<<<dim3((d.hn * d.vn + 255) / 256, d.J), 256, 0, st>>>(ws, d, fc, idxs, rnd, dbg.hyps);
-    CUDA_TRY(cudaGetLastError());
-    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
-    rc = h->score_p == 4 ? launch_score<4>(h, sa, st) : launch_score<3>(h, sa, st);
+    std::vector<Step> steps;
+    steps.reserve(20);
+    if (rnd == 0) {  // K1: compaction and the direction gather
+      if (mask_is_seg)
+        steps.push_back(kstep((const void*)k_seg_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d));
+      else
+        steps.push_back(kstep((const void*)k_mask_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d).arg(vec4));
+      steps.push_back(kstep((const void*)k_scan_tiles, d.J, 128).arg(ws).arg(d));
+      steps.push_back(kstep((const void*)k_job_table, (d.b + 63) / 64, 64).arg(ws).arg(d));
+      steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
+      if ((float)d.hw > p->max_num) steps.push_back(kstep((const void*)k_cap_filter, d.J, 1024).arg(ws).arg(d).arg(selection));
+      steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gather_gx, d.J), 256)
+                          .arg(vertex).arg(ws).arg(d));
+    }
+    steps.push_back(kstep((const void*)k_plan, 1, 1024).arg(ws).arg(d).arg(rnd));
+    steps.push_back(kstep((const void*)k_hypgen, dim3((d.hn * d.vn + 255) / 256, d.J), 256).arg(ws).arg(d).arg(fc).arg(idxs).arg(rnd).arg(dbg.hyps));
+    if (h->timing) steps.push_back(special(STEP_EV0));
+    steps.push_back(kstep(score_fn, h->sm_count * h->score_occ, kScoreThreads).arg(sa));
+    if (h->timing) steps.push_back(special(STEP_EV1));
+    steps.push_back(kstep((const void*)k_update, d.J, 32 * d.vn).arg(ws).arg(d).arg(rnd).arg(dbg));
+    // Refinement and solve are queued BEFORE the host waits for the loop state, so in the common single-round
+    // case the GPU never idles on the round trip; if another round is needed they simply run again after it.
+    steps.push_back(special(STEP_READBACK));
+    steps.push_back(kstep((const void*)k_refine, dim3(refine_gx, d.vn), 256).arg(ws).arg(d).arg(fc));
+    steps.push_back(kstep((const void*)k_solve, d.J, 32).arg(ws).arg(d).arg(out_points).arg(dbg));
+    for (const Step& s : steps) launches += s.kind == STEP_KERNEL;
+    rc = (rnd == 0 && h->use_graph) ? run_graph(h, steps, ws, st) : run_direct(h, steps, ws, st);
     if (rc) return rc;
-    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
-    k_update<<<d.J, upd_threads, 0, st>>>(ws, d, rnd, dbg);
-    launches += 4;
-    CUDA_TRY(cudaGetLastError());
-    // the reference's data-dependent `while` (:318): one 32-byte read-back per round.  Refinement and solve are
-    // enqueued BEFORE the host waits, so in the common single-round case the GPU never idles on the round trip;
-    // if another round turns out to be needed they are simply run again after it (they only read loop state).
-    CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h->pinned_stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(h->ev_round, st));
-    k_refine<<<dim3(refine_gx, d.vn), 256, 0, st>>>(ws, d, fc);
-    k_solve<<<d.J, 32, 0, st>>>(ws, d, out_points, dbg);
-    launches += 2;
-    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventSynchronize(h->ev_round));  // the host waits for the loop state only, not for refine/solve
     ++h->score_launches;
     if (h->timing) {

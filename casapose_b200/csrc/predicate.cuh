@@ -109,6 +109,34 @@ __device__ __forceinline__ void filter_test(const PixCoef& c, float hx, float hy
   hi = (__float_as_uint(thi) >> 31) != 0u;
 }
 
+// ---------------------------------------------------------------- chunk-local form (what k_score evaluates)
+// upper bound of sqrt(x^2 + y^2):  max + (sqrt2 - 1) min  (exact at 0 and 45 degrees, concave in between)
+__device__ __forceinline__ float oct_norm(float x, float y) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  return fmaf(0.4142136f, fminf(ax, ay), fmaxf(ax, ay)) * 1.0000005f;
+}
+
+// Coefficients of one pixel relative to the chunk origin o: (cxl, cyl) = c - o (exact).
+//   A = (D, -E, -P0, A0), B = (-G, -H);  invalid pixels (|d| <= 1e-6): t = +1e30 for every hypothesis.
+// Returns false if the direction cannot use the filter (non-finite / huge).
+__device__ __forceinline__ bool make_local_coef(float cxl, float cyl, float dx, float dy, float k_lo, float4& A, float2& B) {
+  A = make_float4(0.f, 0.f, 0.f, 1.0e30f);
+  B = make_float2(0.f, 0.f);
+  PixCoef pc;
+  if (!make_coef(0.f, 0.f, dx, dy, k_lo, pc)) return false;
+  if (pc.D != 0.f || pc.E != 0.f) {
+    A = make_float4(pc.D, -pc.E, -(pc.D * cyl - pc.E * cxl), pc.G * cxl + pc.H * cyl);
+    B = make_float2(-pc.G, -pc.H);
+  }
+  return true;
+}
+
+// One unit in the chunk-local form, (hxl, hyl) = fl(h - o):  t = |p| + s, inlier <=> sign bit of t.
+__device__ __forceinline__ float local_unit(const float4& A, const float2& B, float hxl, float hyl, float& p) {
+  p = fmaf(A.x, hyl, fmaf(A.y, hxl, A.z));
+  return fabsf(p) + fmaf(B.x, hxl, fmaf(B.y, hyl, A.w));
+}
+
 // 0 = normal (filter), 1 = zero count by construction, 2 = exact list
 __device__ __forceinline__ int classify_hypothesis(float hx, float hy, bool fast_ok) {
   if (!(fabsf(hx) <= 3.0e38f && fabsf(hy) <= 3.0e38f)) return 1;  // inf / NaN: every ang is NaN or 0/inf

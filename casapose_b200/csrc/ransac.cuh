@@ -172,12 +172,6 @@ __device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const 
   return __reduce_add_sync(0xffffffffu, c);
 }
 
-// upper bound of sqrt(x^2 + y^2):  max + (sqrt2 - 1) min  (exact at 0 and 45 degrees, concave in between)
-__device__ __forceinline__ float oct_norm(float x, float y) {
-  const float ax = fabsf(x), ay = fabsf(y);
-  return fmaf(0.4142136f, fminf(ax, ay), fmaxf(ax, ay)) * 1.0000005f;
-}
-
 // Stage 2 of the filter for the two hypotheses (a, b) of a flagged pair: every lane re-evaluates its
 // pixels of the chunk from the shared-memory coefficients with the per-unit band
 //     |t| < kappa |p| + E        (E = evaluation-error bound of that hypothesis in this chunk)
@@ -193,10 +187,9 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
   for (int q = lane; q < npx; q += 32) {
     const float4 A = cA[q];
     const float2 B = cB[q];
-    const float pa = fmaf(A.x, ay, fmaf(A.y, ax, A.z));
-    const float pb = fmaf(A.x, by, fmaf(A.y, bx, A.z));
-    const float ta = fabsf(pa) + fmaf(B.x, ax, fmaf(B.y, ay, A.w));
-    const float tb = fabsf(pb) + fmaf(B.x, bx, fmaf(B.y, by, A.w));
+    float pa, pb;
+    const float ta = local_unit(A, B, ax, ay, pa);
+    const float tb = local_unit(A, B, bx, by, pb);
     const bool ua = fabsf(ta) < fmaf(kappa2, fabsf(pa), ea);
     const bool ub = fabsf(tb) < fmaf(kappa2, fabsf(pb), eb);
     if (ua || ub) {  // ~1e-5 of the units
@@ -299,14 +292,9 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
       float4 A = make_float4(0.f, 0.f, 0.f, 1.0e30f);  // invalid / padding pixel: t = +1e30, never inlier, never flagged
       float2 B = make_float2(0.f, 0.f);
       if (px[k] >= 0) {
-        PixCoef pc;
-        weird |= !make_coef(0.f, 0.f, dvs[k].x, dvs[k].y, a.fc.k_lo, pc);
         const float cxl = ((float)px[k] + 0.5f) - ox, cyl = ((float)py[k] + 0.5f) - oy;  // c' = c - o, exact
         rr = fmaxf(rr, oct_norm(cxl, cyl));
-        if (pc.D != 0.f || pc.E != 0.f) {
-          A = make_float4(pc.D, -pc.E, -(pc.D * cyl - pc.E * cxl), pc.G * cxl + pc.H * cyl);
-          B = make_float2(-pc.G, -pc.H);
-        }
+        weird |= !make_local_coef(cxl, cyl, dvs[k].x, dvs[k].y, a.fc.k_lo, A, B);
       }
       cA[q] = A;
       cB[q] = B;
@@ -349,12 +337,9 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
         const float2 B = cB[q];
 #pragma unroll
         for (int i = 0; i < kHypPerLane; i += 2) {
-          const float p0 = fmaf(A.x, hy[i], fmaf(A.y, hx[i], A.z));
-          const float p1 = fmaf(A.x, hy[i + 1], fmaf(A.y, hx[i + 1], A.z));
-          const float s0 = fmaf(B.x, hx[i], fmaf(B.y, hy[i], A.w));
-          const float s1 = fmaf(B.x, hx[i + 1], fmaf(B.y, hy[i + 1], A.w));
-          const float t0v = fabsf(p0) + s0;
-          const float t1v = fabsf(p1) + s1;
+          float p0, p1;
+          const float t0v = local_unit(A, B, hx[i], hy[i], p0);
+          const float t1v = local_unit(A, B, hx[i + 1], hy[i + 1], p1);
           nlo[i] += __float_as_uint(t0v) >> 31;
           nlo[i + 1] += __float_as_uint(t1v) >> 31;
           mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t0v)), fabsf(t1v));

@@ -192,6 +192,8 @@ int casa_get_timing(casa_handle* h, double* score_ms, int64_t* score_launches, u
  * Self-test of the filtered inlier predicate: draws n adversarial (pixel, hypothesis)
  * pairs concentrated on the decision boundary and compares filter+fallback with the
  * reference-exact float32 sequence (ransac_voting.py:230-249).
+ * spread = half-width (rad) of the sampled band around the boundary; a negative spread additionally draws extreme
+ * magnitudes (coordinates to 65535, |d| in 2^[-19,29], pixel-hypothesis distances 2^[-17,59]).
  * out[0]=tested, out[1]=mismatches, out[2]=sent to exact fallback, out[3]=exact inliers.
  */
 int casa_selftest_filter(casa_handle* h, uint64_t n, uint64_t seed, float inlier_thresh,

@@ -166,7 +166,9 @@ def test_filter_selftest_no_mismatch(cuda_lib):
     from casapose_b200 import _lib
 
     h = _lib.handle(0)
-    for thr, spread in ((0.99, 2e-5), (0.99, 1e-2), (0.9, 2e-5), (0.999, 5e-5), (0.6, 1e-4)):
+    # negative spread = extreme magnitudes (coordinates to 65535, |d| in 2^[-19,29], distances 2^[-17,59])
+    for thr, spread in ((0.99, 2e-5), (0.99, 1e-2), (0.9, 2e-5), (0.999, 5e-5), (0.6, 1e-4), (0.99, -2e-5), (0.99, -1e-3),
+                        (0.75, -5e-5)):
         res = (C.c_uint64 * 4)()
         _lib.check(cuda_lib.casa_selftest_filter(h, 1 << 26, 99, thr, spread, res))
         tested, bad, unc, inl = list(res)

@@ -72,6 +72,8 @@ EXPORTS = {
     "casa_ransac_vote_host": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "casa_ls_vote": (C.c_int, [C.c_void_p, C.POINTER(LsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.POINTER(LsDebug), C.c_void_p]),
+    "casa_pnp": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_void_p]),
     "casa_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "casa_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "casa_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

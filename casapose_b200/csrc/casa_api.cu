@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "compaction.cuh"
 #include "ls_vote.cuh"
+#include "pnp.cuh"
 #include "predicate.cuh"
 #include "ransac.cuh"
 #include "selftest.cuh"
@@ -677,6 +678,25 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
     if (h->last_status & CASA_STATUS_LS_NONFINITE)
       return fail(CASA_ERR_INPUT, "CoordLSVotingWeighted: non-finite R / q / p (the reference asserts here, voting_layers_2d.py:109-121)");
   }
+  return CASA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ PnP
+
+extern "C" int casa_pnp(casa_handle* h, int32_t n, int32_t vn, const float* points2d, const float* points3d,
+                        const float* camera, const float* offsets, float* poses, void* stream) {
+  if (!h) return fail(CASA_ERR_INVALID, "handle is NULL");
+  if (!points2d || !points3d || !camera || !poses) return fail(CASA_ERR_INVALID, "points2d / points3d / camera / poses must not be NULL");
+  if (n < 0 || vn < 6 || vn > 16) return fail(CASA_ERR_INVALID, "n=%d, vn=%d: need n >= 0 and 6 <= vn <= 16", n, vn);
+  if (n == 0) return CASA_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  PnpParams pp;
+  pp.n = n;
+  pp.vn = vn;
+  pp.reproj_px = 12.0f;
+  k_pnp<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(pp, points2d, points3d, camera, offsets, poses);
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches = 1;
   return CASA_OK;
 }
 

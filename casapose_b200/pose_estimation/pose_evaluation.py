@@ -41,7 +41,7 @@ def _eval_points(evaluation_points, object_points_3d_count, object_points_3d, b,
 
 def estimate_and_evaluate_poses(output_seg, target_seg, output_vertex, poses_gt, object_points_3d, camera_data,
                                 diameters, offsets, evaluation_points=None, object_points_3d_count=None,
-                                points_estimated=None, min_num=20, **vote_kw):
+                                points_estimated=None, min_num=20, pnp_backend="cv2", **vote_kw):
     """pose_evaluation.py:11-101 -> ([valid_2d, valid_3d, valid_pose_count, false_positive_mask, err_2d, err_3d,
     missing_object, false_positive_pose], poses [b,oc,3,4], points_estimated [b,oc,vn,2])."""
     b, h, w, c = target_seg.shape
@@ -52,7 +52,8 @@ def estimate_and_evaluate_poses(output_seg, target_seg, output_vertex, poses_gt,
         points_estimated = _vote_from_scores(output_seg, output_vertex, oc, vc, min_num, **vote_kw)
     else:
         points_estimated = points_estimated * torch.tensor([[[[h, w]]]], dtype=torch.float32, device=points_estimated.device)  # :60
-    poses, false_positive_mask = estimate_poses(points_estimated, object_points_3d, camera_data, objects_available, offsets)
+    poses, false_positive_mask = estimate_poses(points_estimated, object_points_3d, camera_data, objects_available, offsets,
+                                                pnp_backend=pnp_backend)
     pts3d, cnt = _eval_points(evaluation_points, object_points_3d_count, object_points_3d, b, oc, ic)
     err_2d, err_3d, valid_2d, valid_3d, missing_object, valid_pose_count, false_positive_pose = evaluate_poses(
         poses, poses_gt, points_estimated, pts3d, cnt, camera_data, diameters, objects_available, 5.0)  # :76-86
@@ -97,7 +98,7 @@ def poses_pnp(points_estimated, seg_estimated, object_points_3d, camera_data, no
 
 
 def pose_estimation(output_seg, target_seg, output_vertex, poses_gt, object_points_3d, camera_data, offsets,
-                    points_estimated=None, min_num=20, **vote_kw):
+                    points_estimated=None, min_num=20, pnp_backend="cv2", **vote_kw):
     """pose_evaluation.py:222-269 -> poses [b,oc,3,4]."""
     b, h, w, c = target_seg.shape
     _, oc, ic, _, _ = poses_gt.shape
@@ -107,5 +108,5 @@ def pose_estimation(output_seg, target_seg, output_vertex, poses_gt, object_poin
         points_estimated = _vote_from_scores(output_seg, output_vertex, oc, vc, min_num, **vote_kw)
     else:
         points_estimated = points_estimated * torch.tensor([[[[h, w]]]], dtype=torch.float32, device=points_estimated.device)
-    poses, _ = estimate_poses(points_estimated, object_points_3d, camera_data, objects_available, offsets)
+    poses, _ = estimate_poses(points_estimated, object_points_3d, camera_data, objects_available, offsets, pnp_backend=pnp_backend)
     return torch.from_numpy(poses)

@@ -217,8 +217,30 @@ def project(xyz, K, RT):
     return xy.astype(f), xyz_proj.astype(f)
 
 
-def estimate_poses(points, keypoints, camera_matrixes, valid_points_filter, offsets):
-    """ransac_voting.py:525-558.
+def pnp_cuda(points_2d, points_3d, camera_matrixes, offsets=None):
+    """Batched GPU PnP (casa_pnp): points_2d [n,vn,2] (x,y), points_3d [n,vn,3], camera_matrixes [n,3,3],
+    offsets [n,10] or None -> poses [n,3,4] float32 on the device of points_2d.  Same guards and sign
+    convention as `pnp` / map_offsets / map_pnp (ransac_voting.py:13-57, 487-514)."""
+    dev = points_2d.device if isinstance(points_2d, torch.Tensor) and points_2d.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+    def put(x):
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.asarray(x, np.float32)))
+        return t.to(device=dev, dtype=torch.float32).contiguous()
+
+    p2, p3, cam = put(points_2d), put(points_3d), put(camera_matrixes)
+    off = put(offsets) if offsets is not None else None
+    n, vn = p2.shape[0], p2.shape[1]
+    out = torch.empty((n, 3, 4), dtype=torch.float32, device=dev)
+    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        rc = _lib.lib().casa_pnp(hdl, n, vn, ptr(p2), ptr(p3), ptr(cam), ptr(off), ptr(out), current_stream_ptr(dev))
+    _lib.check(rc)
+    return out
+
+
+def estimate_poses(points, keypoints, camera_matrixes, valid_points_filter, offsets, pnp_backend="cv2"):
+    """ransac_voting.py:525-558.  pnp_backend="cuda" runs the batched GPU PnP (casa_pnp) instead of the
+    per-object OpenCV calls of the reference (about 1.4 ms per object on the host).
     :param points:             [b,oc,vn,2]
     :param keypoints:          [b,oc,ic,vn,3]
     :param camera_matrixes:    [b,3,3]
@@ -232,6 +254,14 @@ def estimate_poses(points, keypoints, camera_matrixes, valid_points_filter, offs
     valid = _np(valid_points_filter)
     offsets = _np(offsets, np.float32)
     b, oc, ic, vn, _ = keypoints.shape
+    if pnp_backend == "cuda":
+        fp = ((valid == 0) & (points.reshape(b, oc, -1).sum(-1, dtype=np.float32) > 0)).astype(np.float32).sum(axis=0)
+        poses = pnp_cuda(points.reshape(b * oc, vn, 2), keypoints[:, :, 0].reshape(b * oc, vn, 3),
+                         np.broadcast_to(camera_matrixes[:, None], (b, oc, 3, 3)).reshape(b * oc, 3, 3),
+                         np.broadcast_to(offsets[:, None], (b, oc, 10)).reshape(b * oc, 10))
+        return poses.cpu().numpy().reshape(b, oc, 3, 4), (fp[0] if oc == 1 else fp)
+    if pnp_backend != "cv2":
+        raise ValueError("pnp_backend must be 'cv2' or 'cuda'")
     poses = np.zeros((b, oc, 3, 4), np.float32)
     false_positive = np.zeros((b, oc), np.float32)
     for i in range(b):

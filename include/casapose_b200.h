@@ -173,6 +173,21 @@ typedef struct casa_ls_debug {
 int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct,
                  const float* conf, float* out_points, const casa_ls_debug* debug, void* stream);
 
+/*
+ * Batched PnP on the GPU — the step right after the voting path.  Stands in for the
+ * reference's host-side pnp / map_offsets / map_pnp
+ * (/root/reference/casapose/pose_estimation/ransac_voting.py:13-57, 487-514): robust initial pose from point
+ * subsets (OpenCV's randomised EPnP-RANSAC cannot be replayed bit for bit), then the Levenberg-Marquardt
+ * minimum of the reprojection error over ALL points in float64, flip if t_z < 0, zeros if |sum(points)| < 0.01
+ * or on failure.
+ *   points2d device float32 [n,vn,2] (x,y) pixels     points3d device float32 [n,vn,3]
+ *   camera   device float32 [n,3,3] (zero skew)        offsets  device float32 [n,10] or NULL (:494-504)
+ *   poses    device float32 [n,3,4] = [R|t]
+ * vn in 6..16.  Asynchronous on `stream`.
+ */
+int casa_pnp(casa_handle* h, int32_t n, int32_t vn, const float* points2d, const float* points3d,
+             const float* camera, const float* offsets, float* poses, void* stream);
+
 /* Device status word of the last casa_ransac_vote on this handle (CASA_STATUS_* bits). */
 int casa_last_status(casa_handle* h, uint32_t* status);
 /* Number of kernels the last call launched on this handle. */

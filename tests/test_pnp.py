@@ -68,7 +68,7 @@ def test_gpu_pnp_matches_restatement_and_cv2(cuda_lib):
         if i == 5:
             continue
         ref = pnp_np.pnp(X, p2[i], K)
-        assert np.abs(got[i] - ref).max() < 1e-3 * max(1.0, np.abs(ref).max() * 1e-3), i  # same algorithm, float64 both
+        assert np.abs(got[i] - ref).max() < 1e-3, i  # same algorithm, float64 on both sides (mm / rotation entries)
         n_cv += _close(got[i], OP.pnp(X, p2[i], K))
     assert n_cv >= 0.95 * (len(cases) - 1)
 

@@ -74,6 +74,8 @@ EXPORTS = {
                                C.POINTER(LsDebug), C.c_void_p]),
     "casa_pnp": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_void_p]),
+    "casa_pose_errors": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "casa_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "casa_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "casa_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

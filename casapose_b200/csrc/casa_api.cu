@@ -11,6 +11,7 @@
 #include "compaction.cuh"
 #include "ls_vote.cuh"
 #include "pnp.cuh"
+#include "pose_metric.cuh"
 #include "predicate.cuh"
 #include "ransac.cuh"
 #include "selftest.cuh"
@@ -41,6 +42,8 @@ struct casa_handle {
   size_t ws_bytes = 0;
   void* io_mem = nullptr;  // device staging of the host-buffer entry points
   size_t io_bytes = 0;
+  void* metric_mem = nullptr;  // scratch of casa_pose_errors
+  size_t metric_bytes = 0;
   int* pinned = nullptr;   // CTRL_WORDS ints, page-locked
   cudaStream_t own_stream = nullptr, copy_stream = nullptr;
   cudaEvent_t part_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -106,6 +109,7 @@ extern "C" int casa_destroy(casa_handle* h) {
   }
   if (h->ws_mem) cudaFree(h->ws_mem);
   if (h->io_mem) cudaFree(h->io_mem);
+  if (h->metric_mem) cudaFree(h->metric_mem);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->pinned_stats) cudaFreeHost(h->pinned_stats);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -697,6 +701,50 @@ extern "C" int casa_pnp(casa_handle* h, int32_t n, int32_t vn, const float* poin
   k_pnp<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(pp, points2d, points3d, camera, offsets, poses);
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;
+  return CASA_OK;
+}
+
+extern "C" int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t maxp, const float* poses, const float* poses_gt,
+                                const float* camera, const float* model_points, const int32_t* model_counts,
+                                const int32_t* obj_model, const float* diameters, const int32_t* valid,
+                                float allowed_error_2d, float* out_rows, void* stream) {
+  if (!h) return fail(CASA_ERR_INVALID, "handle is NULL");
+  if (!poses || !poses_gt || !camera || !model_points || !model_counts || !diameters || !valid || !out_rows)
+    return fail(CASA_ERR_INVALID, "casa_pose_errors: only obj_model may be NULL");
+  if (n < 0 || m < 1 || maxp < 1) return fail(CASA_ERR_INVALID, "n=%d, m=%d, maxp=%d: need n >= 0, m >= 1, maxp >= 1", n, m, maxp);
+  if (n == 0) return CASA_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  PoseErrParams pp;
+  pp.n = n;
+  pp.m = m;
+  pp.maxp = maxp;
+  pp.allowed_2d = allowed_error_2d;
+  const bool may_sym = maxp >= 3417;  // ADD-S only for the 7862 / 3417 vertex meshes (ransac_voting.py:618)
+  const int tiles = (maxp + kMetricThreads - 1) / kMetricThreads;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t base_b = up((size_t)n * 2 * sizeof(float)), state_b = up((size_t)n * sizeof(int));
+  const size_t part_b = may_sym ? up((size_t)n * tiles * sizeof(double)) : 0;
+  const size_t cloud_b = may_sym ? up((size_t)n * maxp * sizeof(double4)) : 0;
+  int rc = ensure(&h->metric_mem, &h->metric_bytes, base_b + state_b + part_b + 2 * cloud_b);
+  if (rc != CASA_OK) return rc;
+  char* b = (char*)h->metric_mem;
+  float* base = (float*)b;
+  int* state = (int*)(b + base_b);
+  double* partial = (double*)(b + base_b + state_b);
+  double4* cloud_gt = may_sym ? (double4*)(b + base_b + state_b + part_b) : nullptr;
+  double4* cloud_est = may_sym ? (double4*)(b + base_b + state_b + part_b + cloud_b) : nullptr;
+  k_pose_project<<<n, kMetricThreads, 0, st>>>(pp, poses, poses_gt, camera, model_points, model_counts, obj_model, valid,
+                                               cloud_gt, cloud_est, base, state, out_rows);
+  int launches = 1;
+  if (may_sym) {
+    k_adds_min<<<dim3(tiles, n), kMetricThreads, 0, st>>>(pp, model_counts, obj_model, state, cloud_gt, cloud_est, partial);
+    ++launches;
+  }
+  k_pose_finalize<<<(n + 127) / 128, 128, 0, st>>>(pp, tiles, model_counts, obj_model, state, base, partial, diameters, out_rows);
+  ++launches;
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches = launches;
   return CASA_OK;
 }
 

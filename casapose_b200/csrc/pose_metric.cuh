@@ -1,0 +1,180 @@
+// K8 — ADD / ADD-S / 2-D reprojection errors of a batch of poses.
+//
+// Stands in for map_estimates + evaluate_poses
+// (/root/reference/casapose/pose_estimation/ransac_voting.py:561-625, 628-687), which the reference runs as a
+// serial tf.map_fn over (image, class): project the evaluation points with the estimated and the ground-truth
+// pose (project_tf, :173-182, float32), mean 2-D distance, mean 3-D distance (ADD) or — for the two symmetric
+// LINEMOD meshes, recognised by their vertex counts 7862 / 3417 (:618) — the mean closest-point distance
+// (ADD-S) taken from the float64 expansion |a|^2 - 2ab + |b|^2 over all N x N pairs (:596-610).
+//
+//   k_pose_project  one block per object: guards, both projections, err_2d, ADD; symmetric objects leave their
+//                   two point clouds in scratch (float64 xyz + squared norm);
+//   k_adds_min      (256-row tile, object): every thread owns one ground-truth point and scans the estimated
+//                   cloud through shared memory — FP64-FMA-bound, 5 flops per pair;
+//   k_pose_finalize sums the tile partials in order, applies the 0.1*diameter and 2-D thresholds.
+// Output rows are map_estimates' own: [err_2d, err_3d, valid_3d, valid_2d, missing, false_positive].
+#pragma once
+#include "common.cuh"
+
+namespace casa {
+
+constexpr int kMetricThreads = 256;
+constexpr int kAddsTile = 1024;  // estimated points per shared-memory pass
+
+struct PoseErrParams {
+  int n, m, maxp;
+  float allowed_2d;
+};
+
+__device__ __forceinline__ bool adds_symmetric(int count) { return count == 7862 || count == 3417; }  // :618
+
+// sequential float32 sum of the 12 pose entries (tf.reduce_sum(pose), :575-579)
+__device__ __forceinline__ float pose_sum(const float* p) {
+  float s = 0.f;
+  for (int k = 0; k < 12; ++k) s = __fadd_rn(s, p[k]);
+  return s;
+}
+
+// project_tf (:173-182): xyz @ R^T + t, then @ K^T, xy / z  — float32, one rounding per op
+__device__ __forceinline__ void project_point(const float* P, const float* RT, const float* K, float2& uv, float3& c) {
+  c.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], RT[0]), __fmul_rn(P[1], RT[1])), __fmul_rn(P[2], RT[2])), RT[3]);
+  c.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], RT[4]), __fmul_rn(P[1], RT[5])), __fmul_rn(P[2], RT[6])), RT[7]);
+  c.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], RT[8]), __fmul_rn(P[1], RT[9])), __fmul_rn(P[2], RT[10])), RT[11]);
+  const float u = __fadd_rn(__fadd_rn(__fmul_rn(c.x, K[0]), __fmul_rn(c.y, K[1])), __fmul_rn(c.z, K[2]));
+  const float v = __fadd_rn(__fadd_rn(__fmul_rn(c.x, K[3]), __fmul_rn(c.y, K[4])), __fmul_rn(c.z, K[5]));
+  const float w = __fadd_rn(__fadd_rn(__fmul_rn(c.x, K[6]), __fmul_rn(c.y, K[7])), __fmul_rn(c.z, K[8]));
+  uv.x = __fdiv_rn(u, w);
+  uv.y = __fdiv_rn(v, w);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {  // fixed order: deterministic
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  double s = 0;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < kMetricThreads / 32; ++k) s += sh[k];
+  __syncthreads();
+  return s;  // valid in thread 0
+}
+
+// state[obj]: 0 = row already final, 1 = ADD done (err in base), 2 = ADD-S pending
+__global__ void __launch_bounds__(kMetricThreads)
+    k_pose_project(PoseErrParams pp, const float* __restrict__ poses, const float* __restrict__ poses_gt,
+                   const float* __restrict__ cam, const float* __restrict__ model_pts, const int* __restrict__ model_cnt,
+                   const int* __restrict__ obj_model, const int* __restrict__ valid, double4* __restrict__ cloud_gt,
+                   double4* __restrict__ cloud_est, float* __restrict__ base, int* __restrict__ state, float* __restrict__ out) {
+  __shared__ double sh[kMetricThreads / 32];
+  __shared__ float sRT[12], sGT[12], sK[9];
+  const int obj = blockIdx.x;
+  if (threadIdx.x < 12) {
+    sRT[threadIdx.x] = poses[(size_t)obj * 12 + threadIdx.x];
+    sGT[threadIdx.x] = poses_gt[(size_t)obj * 12 + threadIdx.x];
+  }
+  if (threadIdx.x < 9) sK[threadIdx.x] = cam[(size_t)obj * 9 + threadIdx.x];
+  __syncthreads();
+  const float psum = pose_sum(sRT);
+  float* row = out + (size_t)obj * 6;
+  if (valid[obj] == 0) {  // :573-576
+    if (threadIdx.x < 6) row[threadIdx.x] = (threadIdx.x == 5 && fabsf(psum) > 0.0001f) ? 1.f : 0.f;
+    if (threadIdx.x == 0) state[obj] = 0;
+    return;
+  }
+  if (fabsf(psum) < 0.0001f) {  // :577-578 object could not be found at all
+    if (threadIdx.x == 0) {
+      row[0] = 99.9f; row[1] = 999.9f; row[2] = 0.f; row[3] = 0.f; row[4] = 1.f; row[5] = 0.f;
+      state[obj] = 0;
+    }
+    return;
+  }
+  const int model = obj_model ? obj_model[obj] : obj % pp.m;
+  const int cnt = min(model_cnt[model], pp.maxp);
+  const bool sym = adds_symmetric(cnt) && cloud_gt != nullptr;
+  const float* pts = model_pts + (size_t)model * pp.maxp * 3;
+  double e2 = 0, e3 = 0;
+  for (int i = threadIdx.x; i < cnt; i += kMetricThreads) {
+    float2 ue, ug;
+    float3 ce, cg;
+    project_point(pts + 3 * i, sRT, sK, ue, ce);
+    project_point(pts + 3 * i, sGT, sK, ug, cg);
+    const float dx = __fsub_rn(ug.x, ue.x), dy = __fsub_rn(ug.y, ue.y);
+    e2 += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));  // tf.norm(axis=1), :591
+    if (sym) {
+      const double ax = cg.x, ay = cg.y, az = cg.z, bx = ce.x, by = ce.y, bz = ce.z;
+      cloud_gt[(size_t)obj * pp.maxp + i] = make_double4(ax, ay, az, ax * ax + ay * ay + az * az);
+      cloud_est[(size_t)obj * pp.maxp + i] = make_double4(bx, by, bz, bx * bx + by * by + bz * bz);
+    } else {
+      const float a = __fsub_rn(cg.x, ce.x), b = __fsub_rn(cg.y, ce.y), c = __fsub_rn(cg.z, ce.z);
+      e3 += (double)__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));  // :621
+    }
+  }
+  e2 = block_sum(e2, sh);
+  e3 = block_sum(e3, sh);
+  if (threadIdx.x == 0) {
+    base[2 * obj] = (float)(e2 / cnt);
+    base[2 * obj + 1] = (float)(e3 / cnt);
+    state[obj] = sym ? 2 : 1;
+  }
+}
+
+// grid (tiles, n): rows = ground-truth points, scan = estimated points (adds_error(target, estimate), :619)
+__global__ void __launch_bounds__(kMetricThreads)
+    k_adds_min(PoseErrParams pp, const int* __restrict__ model_cnt, const int* __restrict__ obj_model,
+               const int* __restrict__ state, const double4* __restrict__ cloud_gt, const double4* __restrict__ cloud_est,
+               double* __restrict__ partial) {
+  __shared__ double4 sB[kAddsTile];
+  __shared__ double sh[kMetricThreads / 32];
+  const int obj = blockIdx.y;
+  if (state[obj] != 2) return;
+  const int model = obj_model ? obj_model[obj] : obj % pp.m;
+  const int cnt = min(model_cnt[model], pp.maxp);
+  const int row0 = blockIdx.x * kMetricThreads;
+  if (row0 >= cnt) return;
+  const int r = row0 + threadIdx.x;
+  const double4 a = cloud_gt[(size_t)obj * pp.maxp + min(r, cnt - 1)];
+  const double4* B = cloud_est + (size_t)obj * pp.maxp;
+  double best = INFINITY;
+  for (int t0 = 0; t0 < cnt; t0 += kAddsTile) {
+    const int nt = min(kAddsTile, cnt - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nt; k += kMetricThreads) sB[k] = B[t0 + k];
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < nt; ++k) {
+      const double4 b = sB[k];
+      const double dot = a.x * b.x + a.y * b.y + a.z * b.z;
+      best = fmin(best, (a.w - 2.0 * dot) + b.w);  // row_norms_A - 2 A B^T + row_norms_B (:607)
+    }
+  }
+  const double v = r < cnt ? (double)(float)sqrt(fabs(best) + 1e-5) : 0.0;  // :609, cast to float32 per point
+  const double s = block_sum(v, sh);
+  if (threadIdx.x == 0) partial[(size_t)obj * gridDim.x + blockIdx.x] = s;
+}
+
+__global__ void k_pose_finalize(PoseErrParams pp, int tiles, const int* __restrict__ model_cnt, const int* __restrict__ obj_model,
+                                const int* __restrict__ state, const float* __restrict__ base, const double* __restrict__ partial,
+                                const float* __restrict__ diameters, float* __restrict__ out) {
+  const int obj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj >= pp.n || state[obj] == 0) return;
+  const int model = obj_model ? obj_model[obj] : obj % pp.m;
+  const int cnt = min(model_cnt[model], pp.maxp);
+  float e3 = base[2 * obj + 1];
+  if (state[obj] == 2) {
+    double s = 0;
+    const int used = (cnt + kMetricThreads - 1) / kMetricThreads;
+    for (int t = 0; t < used && t < tiles; ++t) s += partial[(size_t)obj * tiles + t];
+    e3 = (float)(s / cnt);
+  }
+  const float e2 = base[2 * obj];
+  float* row = out + (size_t)obj * 6;
+  row[0] = e2;
+  row[1] = e3;
+  row[2] = e3 < __fmul_rn(diameters[obj], 0.1f) ? 1.f : 0.f;  // :623
+  row[3] = e2 < pp.allowed_2d ? 1.f : 0.f;                     // :624
+  row[4] = 0.f;
+  row[5] = 0.f;
+}
+
+}  // namespace casa

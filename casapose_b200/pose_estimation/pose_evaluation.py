@@ -31,7 +31,7 @@ def _objects_available(target_seg, min_num):
 def _eval_points(evaluation_points, object_points_3d_count, object_points_3d, b, oc, ic):
     if evaluation_points is not None and object_points_3d_count is not None:  # :67-72
         ev = _np(evaluation_points, np.float32)[None, :, None]
-        object_points_3d = np.tile(ev, [b, 1, ic, 1, 1])
+        object_points_3d = np.broadcast_to(ev, (b, ev.shape[1], ic) + ev.shape[3:])  # tf.tile (:69), without the copies
         cnt = np.tile(_np(object_points_3d_count)[None], [b, 1, ic])
     else:
         object_points_3d = _np(object_points_3d, np.float32)
@@ -41,7 +41,7 @@ def _eval_points(evaluation_points, object_points_3d_count, object_points_3d, b,
 
 def estimate_and_evaluate_poses(output_seg, target_seg, output_vertex, poses_gt, object_points_3d, camera_data,
                                 diameters, offsets, evaluation_points=None, object_points_3d_count=None,
-                                points_estimated=None, min_num=20, pnp_backend="cv2", **vote_kw):
+                                points_estimated=None, min_num=20, pnp_backend="cv2", metric_backend="numpy", **vote_kw):
     """pose_evaluation.py:11-101 -> ([valid_2d, valid_3d, valid_pose_count, false_positive_mask, err_2d, err_3d,
     missing_object, false_positive_pose], poses [b,oc,3,4], points_estimated [b,oc,vn,2])."""
     b, h, w, c = target_seg.shape
@@ -56,26 +56,27 @@ def estimate_and_evaluate_poses(output_seg, target_seg, output_vertex, poses_gt,
                                                 pnp_backend=pnp_backend)
     pts3d, cnt = _eval_points(evaluation_points, object_points_3d_count, object_points_3d, b, oc, ic)
     err_2d, err_3d, valid_2d, valid_3d, missing_object, valid_pose_count, false_positive_pose = evaluate_poses(
-        poses, poses_gt, points_estimated, pts3d, cnt, camera_data, diameters, objects_available, 5.0)  # :76-86
+        poses, poses_gt, points_estimated, pts3d, cnt, camera_data, diameters, objects_available, 5.0,
+        backend=metric_backend)  # :76-86
     return ([valid_2d, valid_3d, valid_pose_count, false_positive_mask, err_2d, err_3d, missing_object, false_positive_pose],
             torch.from_numpy(poses), points_estimated)
 
 
 def evaluate_pose_estimates(points_estimated, poses, poses_gt, target_seg, object_points_3d, camera_data, diameters,
-                            evaluation_points=None, object_points_3d_count=None, min_num=20):
+                            evaluation_points=None, object_points_3d_count=None, min_num=20, metric_backend="numpy"):
     """pose_evaluation.py:104-160."""
     b, h, w, c = target_seg.shape
     _, oc, ic, _, _ = poses_gt.shape
     objects_available = _objects_available(target_seg, min_num)
     pts3d, cnt = _eval_points(evaluation_points, object_points_3d_count, object_points_3d, b, oc, ic)
     err_2d, err_3d, valid_2d, valid_3d, missing_object, valid_pose_count, false_positive_pose = evaluate_poses(
-        poses, poses_gt, points_estimated, pts3d, cnt, camera_data, diameters, objects_available, 5.0)
+        poses, poses_gt, points_estimated, pts3d, cnt, camera_data, diameters, objects_available, 5.0, backend=metric_backend)
     return ([valid_2d, valid_3d, valid_pose_count, np.zeros_like(valid_2d), err_2d, err_3d, missing_object,
              false_positive_pose], poses, points_estimated)
 
 
-def poses_pnp(points_estimated, seg_estimated, object_points_3d, camera_data, no_objects, min_num=20):
-    """pose_evaluation.py:164-217: LS-layer output (y,x) -> PnP -> [b,oc,1,3,4]."""
+def poses_pnp(points_estimated, seg_estimated, object_points_3d, camera_data, no_objects, min_num=20, pnp_backend="cv2"):
+    """pose_evaluation.py:164-217: LS-layer output (y,x) -> PnP -> [b,oc,1,3,4].  pnp_backend="cuda": casa_pnp."""
     b, h, w, _ = seg_estimated.shape
     oc, ic = no_objects, 1
     _, _, _, vc, _ = object_points_3d.shape
@@ -86,6 +87,15 @@ def poses_pnp(points_estimated, seg_estimated, object_points_3d, camera_data, no
     count = (hot > 0.1).sum(dim=(1, 2))  # :186-188
     available = (count > min_num).to(torch.float32).reshape(-1, 1, 1).cpu().numpy()  # :190-197
     cam = _np(camera_data, np.float32)[0]
+    if pnp_backend == "cuda":
+        from .ransac_voting import pnp_cuda
+
+        n = pts.shape[0]
+        poses = pnp_cuda(np.ascontiguousarray(pts), np.broadcast_to(obj3d, (n,) + obj3d.shape[1:]) if obj3d.shape[0] == n
+                         else np.tile(obj3d, (n // obj3d.shape[0], 1, 1)), np.broadcast_to(cam, (n, 3, 3))).cpu().numpy()
+        return torch.from_numpy((poses * available).reshape(b, oc, ic, 3, 4).astype(np.float32))
+    if pnp_backend != "cv2":
+        raise ValueError("pnp_backend must be 'cv2' or 'cuda'")
     poses6 = BPNP_fast(name="BPNP")([np.ascontiguousarray(pts), obj3d, cam])  # :199
     if not np.isfinite(poses6).all():  # :201-206
         raise FloatingPointError("Tensor had inf or nan values: %r" % (poses6,))

@@ -162,7 +162,7 @@ def _np(x, dtype=None):
     if isinstance(x, torch.Tensor):
         x = x.detach().cpu().numpy()
     x = np.asarray(x)
-    return x.astype(dtype) if dtype is not None else x
+    return x.astype(dtype, copy=False) if dtype is not None else x
 
 
 def pnp(points_3d, points_2d, camera_matrix, method=None):
@@ -309,10 +309,39 @@ def map_estimates(pose, pose_gt, object_points_3d, camera_matrix, diameter, vali
     return np.array([err_2d, err_3d, valid_3d, valid_2d, 0.0, 0.0], np.float32)
 
 
+def pose_errors_cuda(poses, poses_gt, camera_matrixes, model_points, model_counts, diameters, valid, allowed_error_2d=5.0,
+                     obj_model=None):
+    """Per-object rows of map_estimates (ransac_voting.py:561-625) on the GPU (casa_pose_errors).
+    poses, poses_gt [n,3,4]; camera_matrixes [n,3,3]; model_points [m,maxp,3]; model_counts [m]; diameters [n];
+    valid [n]; obj_model [n] or None (object i uses model i % m) -> [n,6] float32 device tensor
+    [err_2d, err_3d, valid_3d, valid_2d, missing, false_positive]."""
+    dev = poses.device if isinstance(poses, torch.Tensor) and poses.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+    def put(x, dtype=torch.float32):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.array(x, copy=True))  # also un-broadcasts read-only views
+        return t.to(device=dev, dtype=dtype).contiguous()
+
+    po, gt, cam = put(poses).reshape(-1, 3, 4), put(poses_gt).reshape(-1, 3, 4), put(camera_matrixes).reshape(-1, 3, 3)
+    pts, cnt = put(model_points), put(model_counts, torch.int32).reshape(-1)
+    dia, val = put(diameters).reshape(-1), put(valid, torch.int32).reshape(-1)
+    om = put(obj_model, torch.int32).reshape(-1) if obj_model is not None else None
+    n, (m, maxp, _) = po.shape[0], pts.shape
+    if not (gt.shape[0] == cam.shape[0] == dia.shape[0] == val.shape[0] == n and cnt.shape[0] == m):
+        raise ValueError("pose_errors_cuda: inconsistent leading dimensions")
+    out = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        rc = _lib.lib().casa_pose_errors(hdl, n, m, maxp, ptr(po), ptr(gt), ptr(cam), ptr(pts), ptr(cnt), ptr(om), ptr(dia),
+                                         ptr(val), float(allowed_error_2d), ptr(out), current_stream_ptr(dev))
+    _lib.check(rc)
+    return out
+
+
 def evaluate_poses(poses, poses_gt, points_estimated, object_points_3d, object_points_3d_count, camera_matrixes,
-                   diameters, valid_points_filter, allowed_error_2d):
+                   diameters, valid_points_filter, allowed_error_2d, backend="numpy"):
     """ransac_voting.py:628-687 -> (err_2d, err_3d, valid_2d, valid_3d, missing_object, valid_points_count,
-    false_positive_detection), each summed over the batch -> [oc]."""
+    false_positive_detection), each summed over the batch -> [oc].  backend="cuda" computes the per-object
+    rows with casa_pose_errors (the N x N ADD-S search is the expensive part on the host)."""
     poses = _np(poses, np.float32)
     poses_gt = _np(poses_gt, np.float32)
     object_points_3d = _np(object_points_3d, np.float32)
@@ -330,6 +359,20 @@ def evaluate_poses(poses, poses_gt, points_estimated, object_points_3d, object_p
         diameters = np.broadcast_to(dm.reshape(1, oc, 1, 1), (b, oc, ic, 1))
     else:
         raise ValueError("diameters must hold b*oc*ic, oc*ic or oc values")
+    if backend == "cuda":
+        same = all(np.array_equal(object_points_3d[0], object_points_3d[i]) and np.array_equal(counts[0], counts[i])
+                   for i in range(1, b)) if object_points_3d.strides[0] != 0 else True
+        if same:  # one model table for the whole batch (how :67-72 tiles it): object (i, c) uses model c
+            table, cnt_t, om = object_points_3d[0, :, 0], counts.reshape(b, oc, ic)[0, :, 0], None
+        else:
+            table, cnt_t, om = object_points_3d[:, :, 0].reshape(b * oc, vn, 3), counts.reshape(b, oc, ic)[:, :, 0].reshape(-1), None
+        res = pose_errors_cuda(poses.reshape(b * oc, 3, 4), poses_gt.reshape(b, oc, ic, 3, 4)[:, :, 0].reshape(b * oc, 3, 4),
+                               np.broadcast_to(cams[:, None], (b, oc, 3, 3)).reshape(b * oc, 3, 3), table, cnt_t,
+                               diameters[:, :, 0, 0].reshape(-1), valid.reshape(-1), allowed_error_2d, om)
+        s = res.reshape(b, oc, 6).sum(dim=0).cpu().numpy()
+        return s[:, 0], s[:, 1], s[:, 3], s[:, 2], s[:, 4], valid.sum(axis=0).astype(np.float32), s[:, 5]
+    if backend != "numpy":
+        raise ValueError("backend must be 'numpy' or 'cuda'")
     res = np.zeros((b, oc, 6), np.float32)
     for i in range(b):
         for c in range(oc):

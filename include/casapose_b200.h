@@ -188,6 +188,24 @@ int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float* seg, cons
 int casa_pnp(casa_handle* h, int32_t n, int32_t vn, const float* points2d, const float* points3d,
              const float* camera, const float* offsets, float* poses, void* stream);
 
+/*
+ * ADD / ADD-S / 2-D reprojection errors of a batch of poses.  Stands in for the reference's
+ * map_estimates + evaluate_poses (/root/reference/casapose/pose_estimation/ransac_voting.py:561-625, 628-687):
+ * per object one row [err_2d, err_3d, valid_3d, valid_2d, missing, false_positive]; the caller sums rows over
+ * the batch like :668-675.  err_3d is the mean point distance (ADD) or, for models with 7862 / 3417 points
+ * (:618), the mean closest-point distance from the float64 expansion of :596-610 (ADD-S).
+ *   poses, poses_gt device float32 [n,3,4]            camera       device float32 [n,3,3]
+ *   model_points    device float32 [m,maxp,3]         model_counts device int32   [m]  points used per model
+ *   obj_model       device int32   [n] model of each object, or NULL: object i uses model i % m
+ *   diameters       device float32 [n]                valid        device int32   [n]  valid_points_filter
+ *   out_rows        device float32 [n,6]
+ * Asynchronous on `stream`; scratch is owned by the handle.
+ */
+int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t maxp, const float* poses, const float* poses_gt,
+                     const float* camera, const float* model_points, const int32_t* model_counts,
+                     const int32_t* obj_model, const float* diameters, const int32_t* valid,
+                     float allowed_error_2d, float* out_rows, void* stream);
+
 /* Device status word of the last casa_ransac_vote on this handle (CASA_STATUS_* bits). */
 int casa_last_status(casa_handle* h, uint32_t* status);
 /* Number of kernels the last call launched on this handle. */

@@ -182,6 +182,18 @@ def run_ls(args):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
+    # backward (casa_ls_vote_backward: forward recomputation + adjoint + one pass over the listed pixels + zero fill)
+    gout = torch.randn((B, OC, VN, 2), device="cuda")
+    for _ in range(3):
+        layer.backward([seg, direct, conf], gout)
+    torch.cuda.synchronize()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(args.steps):
+        layer.backward([seg, direct, conf], gout)
+    b1.record()
+    torch.cuda.synchronize()
+    bwd_ms = b0.elapsed_time(b1) / args.steps
     alg_bytes = B * H * W * 4 * ((1 + OC) + 2 * VN + VN)  # 44.2 MB per frame at oc = 8
     peak = None
     try:
@@ -205,6 +217,9 @@ def run_ls(args):
         "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
                          "sample": "numpy oracle, 1 frame, %.2f s" % cpu_s},
         "gpu_launches": 12 * args.steps,
+        "backward": {"ms_per_step": bwd_ms, "frames_per_s": B / (bwd_ms * 1e-3),
+                     "note": "forward recomputation + gradients w.r.t. direct and confidence logits (dense, zero-filled)",
+                     "bytes_written": B * H * W * 4 * 3 * VN},
     }))
 
 

@@ -72,6 +72,8 @@ EXPORTS = {
     "casa_ransac_vote_host": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "casa_ls_vote": (C.c_int, [C.c_void_p, C.POINTER(LsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.POINTER(LsDebug), C.c_void_p]),
+    "casa_ls_vote_backward": (C.c_int, [C.c_void_p, C.POINTER(LsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "casa_pnp": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_void_p]),
     "casa_pose_errors": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

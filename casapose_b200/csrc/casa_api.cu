@@ -591,10 +591,39 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
 
 // ------------------------------------------------------------------------------------------------ LS layer
 
+namespace {
+struct LsGrad {
+  const float* grad_points = nullptr;  // [b,oc,vn,2]
+  float* grad_direct = nullptr;        // [b,h,w,2*vn]
+  float* grad_conf = nullptr;          // [b,h,w,vn]
+};
+int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct, const float* conf,
+                 float* out_points, const casa_ls_debug* debug, void* stream, const LsGrad* grad);
+}  // namespace
+
 extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct,
                             const float* conf, float* out_points, const casa_ls_debug* debug, void* stream) {
   if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
   if (!seg || !direct || !conf || !out_points) return fail(CASA_ERR_INVALID, "seg / direct / conf / out_points must not be NULL");
+  return ls_vote_impl(h, p, seg, direct, conf, out_points, debug, stream, nullptr);
+}
+
+extern "C" int casa_ls_vote_backward(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct,
+                                     const float* conf, const float* grad_points, float* out_points, float* grad_direct,
+                                     float* grad_conf, void* stream) {
+  if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
+  if (!seg || !direct || !conf || !grad_points || !grad_direct || !grad_conf)
+    return fail(CASA_ERR_INVALID, "casa_ls_vote_backward: only out_points may be NULL");
+  LsGrad g;
+  g.grad_points = grad_points;
+  g.grad_direct = grad_direct;
+  g.grad_conf = grad_conf;
+  return ls_vote_impl(h, p, seg, direct, conf, out_points, nullptr, stream, &g);
+}
+
+namespace {
+int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct, const float* conf,
+                 float* out_points, const casa_ls_debug* debug, void* stream, const LsGrad* grad) {
   if (p->num_classes < 2 || p->num_classes > 33) return fail(CASA_ERR_INVALID, "num_classes=%d outside 2..33", p->num_classes);
   casa_ransac_params rp;
   memset(&rp, 0, sizeof(rp));
@@ -610,7 +639,8 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
   size_t cur = L.total;
   const size_t off_cls9 = bump(cur, npx), off_parent = bump(cur, npx * 4), off_count = bump(cur, npx * 4),
                off_roots = bump(cur, npx * 4), off_nroots = bump(cur, (size_t)d.b * 4), off_sel = bump(cur, (size_t)d.J * 4),
-               off_wt = bump(cur, (size_t)d.b * d.cap * 4), off_cconf = bump(cur, (size_t)d.b * d.cap * d.vn * 4);
+               off_wt = bump(cur, (size_t)d.b * d.cap * 4), off_cconf = bump(cur, (size_t)d.b * d.cap * d.vn * 4),
+               off_adj = bump(cur, (size_t)d.J * d.vn * 6 * 4), off_tmp_out = bump(cur, (size_t)d.J * d.vn * 2 * 4);
   rc = ensure(&h->ws_mem, &h->ws_bytes, cur);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -667,8 +697,17 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
     launches += 2;
   }
   k_ls_reduce<<<dim3(grid_x, d.vn), 256, 0, st>>>(ws, d, lw, ld);
+  if (!out_points) out_points = (float*)(base + off_tmp_out);
   k_ls_solve<<<d.J, 32, 0, st>>>(ws, d, ld, out_points, dbg.sums);
   launches += 2;
+  if (grad) {
+    float* adj = (float*)(base + off_adj);
+    CUDA_TRY(cudaMemsetAsync(grad->grad_direct, 0, npx * 2 * d.vn * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(grad->grad_conf, 0, npx * d.vn * sizeof(float), st));
+    k_ls_adjoint<<<d.J, 32, 0, st>>>(ws, d, ld, grad->grad_points, adj);
+    k_ls_backward<<<grid_x, 256, 0, st>>>(ws, d, lw, ld, adj, grad->grad_direct, grad->grad_conf);
+    launches += 2;
+  }
   CUDA_TRY(cudaGetLastError());
   if (dbg.labels) CUDA_TRY(cudaMemcpyAsync(dbg.labels, lw.cls9, npx, cudaMemcpyDeviceToDevice, st));
   if (dbg.parent && ld.filter) CUDA_TRY(cudaMemcpyAsync(dbg.parent, lw.parent, npx * 4, cudaMemcpyDeviceToDevice, st));
@@ -684,6 +723,7 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
   }
   return CASA_OK;
 }
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------ PnP
 

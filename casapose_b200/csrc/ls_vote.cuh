@@ -468,4 +468,114 @@ __global__ void __launch_bounds__(32) k_ls_solve(WS ws, Dims d, LsDims ld, float
     for (int k = 0; k < 5; ++k) dbg_sums[((size_t)job * d.vn + v) * 5 + k] = acc[k];
 }
 
+// ---------------------------------------------------------------------------------------------- backward
+// Gradient of the layer output w.r.t. `direct` and the confidence logits (the layer is
+// differentiated at /root/reference/train_casapose.py:536-595, seg is behind tf.stop_gradient :37).
+//
+// k_ls_adjoint: per (job, keypoint), float64.  With A = sum hot*R, b = sum hot*q, P = pinv(A), x = P b and the
+// incoming g = dL/dp = grad_out * height (:122):   dL/db = P g =: lam;   dL/dA = -lam x^T + v u^T + r s^T with
+// u = P lam, v = (I - A P) b, r = P x, s = (I - A P) g  (differential of the pseudo-inverse at constant rank; the
+// last two terms vanish when A is invertible).  Stored as float32 — the gradient passes back through the
+// float32 -> float64 casts of :113-114.
+__global__ void __launch_bounds__(32) k_ls_adjoint(WS ws, Dims d, LsDims ld, const float* __restrict__ grad_out,
+                                                   float* __restrict__ adj) {
+  const int job = blockIdx.x, v = threadIdx.x;
+  if (v >= d.vn) return;
+  const int r0 = ws.rtile_start[job], r1 = ws.rtile_start[job + 1];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int rt = r0; rt < r1; ++rt)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] += ws.partial[((size_t)rt * d.vn + v) * 5 + k];
+  const double a = acc[0], b = acc[1], c = acc[2], q0 = acc[3], q1 = acc[4];
+  double P00, P10, P01, P11;
+  pinv2x2_apply(a, b, c, 1.0, 0.0, P00, P10);
+  pinv2x2_apply(a, b, c, 0.0, 1.0, P01, P11);
+  const float2 go = reinterpret_cast<const float2*>(grad_out)[(size_t)job * d.vn + v];
+  const double g0 = (double)__fmul_rn(go.x, (float)ld.h), g1 = (double)__fmul_rn(go.y, (float)ld.h);
+  const double x0 = P00 * q0 + P01 * q1, x1 = P10 * q0 + P11 * q1;
+  const double l0 = P00 * g0 + P10 * g1, l1 = P01 * g0 + P11 * g1;  // P^T g
+  // I - A P (A symmetric)
+  const double e00 = 1.0 - (a * P00 + b * P10), e01 = -(a * P01 + b * P11);
+  const double e10 = -(b * P00 + c * P10), e11 = 1.0 - (b * P01 + c * P11);
+  const double u0 = P00 * l0 + P01 * l1, u1 = P10 * l0 + P11 * l1;          // P P^T g
+  const double v0 = e00 * q0 + e01 * q1, v1 = e10 * q0 + e11 * q1;          // (I - A P) b
+  const double rr0 = P00 * x0 + P10 * x1, rr1 = P01 * x0 + P11 * x1;        // P^T P b
+  const double s0 = e00 * g0 + e10 * g1, s1 = e01 * g0 + e11 * g1;          // (I - P A)^T g = (I - A P)^T g ... transposed index
+  float* o = adj + ((size_t)job * d.vn + v) * 6;
+  o[0] = (float)(-l0 * x0 + v0 * u0 + rr0 * s0);
+  o[1] = (float)(-l0 * x1 + v0 * u1 + rr0 * s1);
+  o[2] = (float)(-l1 * x0 + v1 * u0 + rr1 * s0);
+  o[3] = (float)(-l1 * x1 + v1 * u1 + rr1 * s1);
+  o[4] = (float)l0;
+  o[5] = (float)l1;
+}
+
+// blockIdx.x strides over the refinement tiles (all keypoints per thread: 72 + 36 contiguous bytes per pixel).
+// grad_direct [b,h,w,2*vn] and grad_conf [b,h,w,vn] must be zero-filled; pixels listed for one class are
+// stored, pixels listed for several (near-tie logits) are accumulated atomically.
+__global__ void __launch_bounds__(256) k_ls_backward(WS ws, Dims d, LsWS lw, LsDims ld, const float* __restrict__ adj,
+                                                     float* __restrict__ grad_direct, float* __restrict__ grad_conf) {
+  const int tid = threadIdx.x;
+  const int n_rtiles = ws.rtile_start[d.J];
+  __shared__ float sadj[32 * 6];
+  const float fh = (float)ld.h;
+  for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
+    int lo = 0, hi = d.J;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ws.rtile_start[mid] <= rt) lo = mid; else hi = mid;
+    }
+    const int job = lo, tile = rt - ws.rtile_start[job];
+    const int tn = ws.job_tn[job];
+    const int img = job / d.oc;
+    const size_t base = (size_t)img * d.cap + ws.job_off[job];
+    __syncthreads();
+    if (tid < d.vn * 6) sadj[tid] = adj[(size_t)job * d.vn * 6 + tid];
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < kRefineTile / 256; ++k) {
+      const int t = tile * kRefineTile + k * 256 + tid;
+      if (t >= tn) continue;
+      const float hw = lw.wt[base + t];
+      if (hw == 0.f) continue;  // multiply_no_nan: no gradient through pixels with hot == 0
+      const uint32_t pk = ws.pix[base + t];
+      const int x = pk & 0xFFFFu, y = pk >> 16;
+      const size_t p = (size_t)img * ld.hw + (size_t)y * ld.w + x;
+      const bool shared_px = __popc(ws.bits[p]) > 1;
+      const float cy = __fdiv_rn(__fadd_rn((float)y, 0.5f), fh), cx = __fdiv_rn(__fadd_rn((float)x, 0.5f), fh);
+      for (int v = 0; v < d.vn; ++v) {
+        const float2 dv = __ldg(ws.vdir + base * d.vn + (size_t)v * tn + t);
+        const float wc = lw.cconf[base * d.vn + (size_t)v * tn + t];
+        const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dv.x, dv.x), __fmul_rn(dv.y, dv.y)));
+        const float inv = nrm != 0.f ? __fdiv_rn(1.0f, nrm) : 0.f;
+        const float n0 = dv.x * inv, n1 = dv.y * inv;
+        const float* A = sadj + v * 6;
+        // G = hot * (Abar + lam p^T): gradient w.r.t. R_full of this pixel (:103-108)
+        const float G00 = hw * (A[0] + A[4] * cy), G01 = hw * (A[1] + A[4] * cx);
+        const float G10 = hw * (A[2] + A[5] * cy), G11 = hw * (A[3] + A[5] * cx);
+        const float M00 = 1.0f - n0 * n0, M01 = -n0 * n1, M11 = 1.0f - n1 * n1;
+        const float gw = G00 * M00 + (G01 + G10) * M01 + G11 * M11;  // d/dw of R_full = M * w (:94)
+        // M = I - n n^T (:92-93): dL/dn = -(G_M + G_M^T) n, G_M = w G
+        const float gn0 = -wc * (2.0f * G00 * n0 + (G01 + G10) * n1);
+        const float gn1 = -wc * ((G01 + G10) * n0 + 2.0f * G11 * n1);
+        // n = d / |d| (:89-90): dL/dd = (gn - (gn . n) n) / |d|; zero vector -> zero gradient (divide_no_nan)
+        const float dot = gn0 * n0 + gn1 * n1;
+        const float gd0 = (gn0 - dot * n0) * inv, gd1 = (gn1 - dot * n1) * inv;
+        // softplus' = sigmoid = 1 - exp(-softplus) (:35);  sigmoid' = s (1 - s) (:33)
+        const float gc = gw * (ld.sigmoid_weights ? wc * (1.0f - wc) : -expm1f(-wc));
+        float* gdp = grad_direct + p * (size_t)(2 * d.vn) + 2 * v;
+        float* gcp = grad_conf + p * (size_t)d.vn + v;
+        if (shared_px) {
+          atomicAdd(gdp, gd0);
+          atomicAdd(gdp + 1, gd1);
+          atomicAdd(gcp, gc);
+        } else {
+          *reinterpret_cast<float2*>(gdp) = make_float2(gd0, gd1);
+          *gcp = gc;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace casa

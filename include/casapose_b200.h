@@ -174,6 +174,21 @@ int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float* seg, cons
                  const float* conf, float* out_points, const casa_ls_debug* debug, void* stream);
 
 /*
+ * Backward of CoordLSVotingWeighted w.r.t. `direct` and the confidence logits — what TF's
+ * autodiff produces for the layer inside the training step (/root/reference/train_casapose.py:536-595);
+ * `seg` is behind tf.stop_gradient (voting_layers_2d.py:37) and receives no gradient.  Re-runs the forward
+ * (stateless), then the closed-form adjoint of the 2x2 pseudo-inverse solve and one pass over the listed pixels.
+ *   grad_points device float32 [b,oc,vn,2]   dL/d(output), (y,x) order like the output
+ *   out_points  device float32 [b,oc,vn,2]   forward result, or NULL
+ *   grad_direct device float32 [b,h,w,2*vn]  written (zero where no class is hot)
+ *   grad_conf   device float32 [b,h,w,vn]    written
+ * A zero direction vector gets a zero gradient (TensorFlow's sqrt gradient yields NaN there).
+ */
+int casa_ls_vote_backward(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct,
+                          const float* conf, const float* grad_points, float* out_points, float* grad_direct,
+                          float* grad_conf, void* stream);
+
+/*
  * Batched PnP on the GPU — the step right after the voting path.  Stands in for the
  * reference's host-side pnp / map_offsets / map_pnp
  * (/root/reference/casapose/pose_estimation/ransac_voting.py:13-57, 487-514): robust initial pose from point

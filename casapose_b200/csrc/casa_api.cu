@@ -434,6 +434,8 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     else
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<3>, kScoreThreads, 0));
     if (h->score_occ < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
+    const char* bps = getenv("CASA_SCORE_BPS");  // cap on resident scoring blocks per SM (experiments)
+    if (bps && atoi(bps) >= 1 && atoi(bps) < h->score_occ) h->score_occ = atoi(bps);
   }
   const void* score_fn = h->score_p == 4 ? (const void*)k_score<4> : (const void*)k_score<3>;
   const int refine_gx = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
@@ -876,6 +878,11 @@ extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflop
       case 30: k_fma_peak<30><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       case 31: k_fma_peak<31><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       case 40: k_fma_peak<40><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 50: k_fma_peak<50><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 51: k_fma_peak<51><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 52: k_fma_peak<52><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 53: k_fma_peak<53><<<blocks, 256>>>(dout, iters, 1e-9f); break;
+      case 54: k_fma_peak<54><<<blocks, 256>>>(dout, iters, 1e-9f); break;
       default: return fail(CASA_ERR_INVALID, "unknown fp32 peak variant %d", variant);
     }
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
@@ -886,7 +893,8 @@ extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflop
   }
   CUDA_TRY(cudaFree(dout));
   // variants 0-2: 16 FMA = 32 FLOP per thread-iteration; variant 3: 16 units x 11 algorithmic FLOP
-  const double flop_per_iter = variant <= 2 ? 32.0 : 16.0 * 11.0;
+  // variant 50: 8 m16n8k8 MMAs per warp-iteration = 512 FLOP per thread; 51-53: 1024 units per warp-iteration
+  const double flop_per_iter = variant <= 2 ? 32.0 : variant == 50 ? 512.0 : variant >= 51 ? 32.0 * 11.0 : 16.0 * 11.0;
   *tflops = (double)blocks * 256.0 * iters * flop_per_iter / (best * 1e-3) / 1e12;
   if (ms_out) *ms_out = best;
   return CASA_OK;

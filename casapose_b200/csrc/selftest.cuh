@@ -226,6 +226,129 @@ __device__ __forceinline__ unsigned mix_packed(int iters, float a, float b) {
   return tot;
 }
 
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.0f));
+}
+__device__ __forceinline__ void mma_tf32_acc(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// VARIANT 50: legacy tensor path alone — 8 independent m16n8k8 TF32 accumulator chains per warp
+__device__ __forceinline__ unsigned mix_mma_peak(int iters, float a, float b) {
+  float acc[8][4];
+  unsigned A[4], B[2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) A[k] = __float_as_uint(a + (float)k) & 0xffffe000u;
+  B[0] = __float_as_uint(b) & 0xffffe000u;
+  B[1] = __float_as_uint(b + 1.0f) & 0xffffe000u;
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[n][k] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) mma_tf32_acc(acc[n], A, B);
+  }
+  unsigned tot = 0;
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tot += __float_as_uint(acc[n][k]);
+  return tot;
+}
+
+// VARIANT 51/52/53: the scoring loop with the two linear forms on the legacy tensor path (3xTF32 split, K = 8):
+// per iteration one 16-pixel tile against 64 hypotheses (8 N-tiles): 16 MMAs, then per lane 32 units of
+// |p| + s, sign count, min tracking.  EPI 0: full epilogue, 1: no min, 2: no count / no min (xor keeps t alive)
+template <int EPI>
+__device__ __forceinline__ unsigned mix_mma_loop(int iters, float a, float b, const float4* sm) {
+  unsigned bp[8][2], bs[8][2], nlo[8][2];
+  float mn[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    bp[n][0] = __float_as_uint(a * (float)(n + 1)) & 0xffffe000u;
+    bp[n][1] = __float_as_uint(b + (float)n) & 0xffffe000u;
+    bs[n][0] = __float_as_uint(b * (float)(n + 2)) & 0xffffe000u;
+    bs[n][1] = __float_as_uint(a - (float)n) & 0xffffe000u;
+    nlo[n][0] = nlo[n][1] = 0u;
+    mn[n] = 3.0e38f;
+  }
+  const int lane = threadIdx.x & 31;
+  for (int it = 0; it < iters; ++it) {
+    const float4 fa = sm[((it & 7) * 2) * 32 + lane], fb = sm[((it & 7) * 2 + 1) * 32 + lane];
+    const unsigned ap[4] = {__float_as_uint(fa.x), __float_as_uint(fa.y), __float_as_uint(fa.z), __float_as_uint(fa.w)};
+    const unsigned as[4] = {__float_as_uint(fb.x), __float_as_uint(fb.y), __float_as_uint(fb.z), __float_as_uint(fb.w)};
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      float cp[4], cs[4];
+      mma_tf32(cp, ap, bp[n]);
+      mma_tf32(cs, as, bs[n]);
+      float t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = fabsf(cp[j]) + cs[j];
+      if (EPI <= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nlo[n][j & 1] += __float_as_uint(t[j]) >> 31;
+      } else {
+        nlo[n][0] ^= __float_as_uint(t[0] + t[2]);
+        nlo[n][1] ^= __float_as_uint(t[1] + t[3]);
+      }
+      if (EPI == 0) {
+        mn[n] = fminf(fminf(mn[n], fabsf(t[0])), fabsf(t[1]));
+        mn[n] = fminf(fminf(mn[n], fabsf(t[2])), fabsf(t[3]));
+      }
+    }
+  }
+  unsigned tot = 0;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) tot += nlo[n][0] + nlo[n][1] + __float_as_uint(mn[n]);
+  return tot;
+}
+
+// VARIANT 54: hybrid — s on the tensor path (one MMA per 16 x 8 tile), p as two FFMAs per unit in the fragment layout
+// (lane owns rows g, g+8 and columns 2t, 2t+1 of every tile)
+__device__ __forceinline__ unsigned mix_mma_hybrid(int iters, float a, float b, const float4* sm) {
+  unsigned bs[8][2], nlo[8][2];
+  float hx[8][2], hy[8][2], mn[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    bs[n][0] = __float_as_uint(b * (float)(n + 2)) & 0xffffe000u;
+    bs[n][1] = __float_as_uint(a - (float)n) & 0xffffe000u;
+    hx[n][0] = a * (float)(n + 1); hx[n][1] = a * (float)(n + 3);
+    hy[n][0] = b + (float)n;       hy[n][1] = b - (float)n;
+    nlo[n][0] = nlo[n][1] = 0u;
+    mn[n] = 3.0e38f;
+  }
+  const int lane = threadIdx.x & 31;
+  for (int it = 0; it < iters; ++it) {
+    const float4 fb = sm[((it & 7) * 2 + 1) * 32 + lane];
+    const float4 c0 = sm[((it & 7) * 2) * 32 + (lane >> 2)];      // (D, -E, -P0, .) of row g
+    const float4 c1 = sm[((it & 7) * 2) * 32 + 8 + (lane >> 2)];  // row g + 8
+    const unsigned as[4] = {__float_as_uint(fb.x), __float_as_uint(fb.y), __float_as_uint(fb.z), __float_as_uint(fb.w)};
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      float cs[4], t[4];
+      mma_tf32(cs, as, bs[n]);
+      t[0] = fabsf(fmaf(c0.x, hy[n][0], fmaf(c0.y, hx[n][0], c0.z))) + cs[0];
+      t[1] = fabsf(fmaf(c0.x, hy[n][1], fmaf(c0.y, hx[n][1], c0.z))) + cs[1];
+      t[2] = fabsf(fmaf(c1.x, hy[n][0], fmaf(c1.y, hx[n][0], c1.z))) + cs[2];
+      t[3] = fabsf(fmaf(c1.x, hy[n][1], fmaf(c1.y, hx[n][1], c1.z))) + cs[3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nlo[n][j & 1] += __float_as_uint(t[j]) >> 31;
+      mn[n] = fminf(fminf(mn[n], fabsf(t[0])), fabsf(t[1]));
+      mn[n] = fminf(fminf(mn[n], fabsf(t[2])), fabsf(t[3]));
+    }
+  }
+  unsigned tot = 0;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) tot += nlo[n][0] + nlo[n][1] + __float_as_uint(mn[n]);
+  return tot;
+}
+
 // VARIANT 0: FFMA, 16 independent chains, 2 shared operands
 // VARIANT 1: FFMA2 (fma.rn.f32x2), 8 independent float2 chains
 // VARIANT 2: FFMA with three distinct register operands per instruction
@@ -234,7 +357,26 @@ template <int VARIANT>
 __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float seedv) {
   const float a = 1.0f + seedv * (float)threadIdx.x, b = seedv;
   float r = 0.f;
-  if (VARIANT == 0) {
+  __shared__ float4 smix[16 * 32];
+  if (VARIANT >= 51 && VARIANT <= 54) {
+    for (int k = threadIdx.x; k < 16 * 32; k += 256) {
+      const float v = 0.001f * (float)k + seedv;
+      smix[k] = make_float4(__uint_as_float(__float_as_uint(v) & 0xffffe000u), __uint_as_float(__float_as_uint(-v) & 0xffffe000u),
+                            __uint_as_float(__float_as_uint(v + 1.f) & 0xffffe000u), __uint_as_float(__float_as_uint(0.5f - v) & 0xffffe000u));
+    }
+    __syncthreads();
+  }
+  if (VARIANT == 50) {
+    r = __uint_as_float(mix_mma_peak(iters, a, b));
+  } else if (VARIANT == 51) {
+    r = __uint_as_float(mix_mma_loop<0>(iters, a, b, smix));
+  } else if (VARIANT == 52) {
+    r = __uint_as_float(mix_mma_loop<1>(iters, a, b, smix));
+  } else if (VARIANT == 53) {
+    r = __uint_as_float(mix_mma_loop<2>(iters, a, b, smix));
+  } else if (VARIANT == 54) {
+    r = __uint_as_float(mix_mma_hybrid(iters, a, b, smix));
+  } else if (VARIANT == 0) {
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = (float)k;

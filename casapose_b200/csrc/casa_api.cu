@@ -457,7 +457,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
       steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gather_gx, d.J), 256)
                           .arg(vertex).arg(ws).arg(d));
     }
-    steps.push_back(kstep((const void*)k_plan, 1, 1024).arg(ws).arg(d).arg(rnd));
+    steps.push_back(kstep((const void*)k_plan, 1, 256).arg(ws).arg(d).arg(rnd));
     steps.push_back(kstep((const void*)k_hypgen, dim3((d.hn * d.vn + 255) / 256, d.J), 256).arg(ws).arg(d).arg(fc).arg(idxs).arg(rnd).arg(dbg.hyps));
     if (h->timing) steps.push_back(special(STEP_EV0));
     steps.push_back(kstep(score_fn, h->sm_count * h->score_occ, kScoreThreads).arg(sa));
@@ -679,7 +679,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
   k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
   k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
-  k_plan<<<1, 1024, 0, st>>>(ws, d, 0);
+  k_plan<<<1, 256, 0, st>>>(ws, d, 0);
   launches += 5;
   if (ld.filter) {
     k_cc_init<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
 }
 
 // ------------------------------------------------------------------------------------ plan
-// single block: item_start[j] = sum over active jobs j' < j of ceil(tn/128) * vn;  (round 0 only)
+// single block (any multiple of 32 threads up to 1024): item_start[j] = sum over active jobs j' < j of ceil(tn/128) * vn;  (round 0 only)
 // rtile_start[j] = sum over live jobs of ceil(tn/1024)
 __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
   __shared__ int srun[2];
   if (tid < 2) srun[tid] = 0;
   __syncthreads();
-  for (int s = 0; s < d.J; s += 1024) {
+  for (int s = 0; s < d.J; s += (int)blockDim.x) {
     const int job = s + tid;
     int ci = 0, cr = 0;
     if (job < d.J) {
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
       if (rnd == 0) ws.rtile_start[job] = rr + wr + xr - cr;
     }
     __syncthreads();
-    if (tid == 1023) {
+    if (tid == (int)blockDim.x - 1) {
       srun[0] = ri + wi + xi;
       srun[1] = rr + wr + xr;
     }

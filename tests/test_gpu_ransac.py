@@ -109,6 +109,28 @@ def test_image_offset_makes_sharding_invisible(vote):
     assert torch.equal(full[2], part[0])
 
 
+@pytest.mark.parametrize("variant", ["easy", "hard"])
+def test_graph_replay_equals_debug_path_and_oracle(vote, variant):
+    """Calls without debug outputs replay a cached CUDA graph whose kernel nodes are patched per call; calls with
+    debug outputs launch directly.  Same bits either way, in the multi-round case too, for repeated calls and for
+    a shifted / split batch."""
+    d = synthetic.make_frames(3, 120, 160, (1, 5, 6), variant=variant)
+    mask = np.tile(d["mask"], (3, 1, 1, 1))
+    vertex = np.tile(d["vertex"], (3, 1, 1, 1, 1))
+    mask[7] = 0.0  # an image without any object
+    mi = 6 if variant == "hard" else 20
+    single, dbg, _, rdbg = _compare(vote, mask, vertex, 64, seed=5, max_iter=mi)
+    if variant == "hard":
+        assert max(r["rounds"] for row in rdbg for r in row) > 1
+    m, v = torch.from_numpy(mask).cuda(), torch.from_numpy(vertex).cuda()
+    for _ in range(3):  # first call builds the graph, later calls patch its kernel nodes
+        again = vote(m, v, 64, seed=5, max_iter=mi)
+        assert torch.equal(again, single)
+    shifted = vote(m, v, 64, seed=5, max_iter=mi, image_offset=3)
+    part = vote(m[5:].contiguous(), v[5:].contiguous(), 64, seed=5, max_iter=mi, image_offset=8)
+    assert torch.equal(shifted[5:], part)
+
+
 def test_degenerate_inputs(vote):
     h, w = 64, 80
     mask = np.zeros((1, h, w, 4), np.float32)

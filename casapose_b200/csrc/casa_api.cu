@@ -131,7 +131,7 @@ struct Layout {
   Dims d;
   size_t off_bits, off_tile_cnt, off_tile_base, off_pix, off_vdir, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
       off_job_rounds, off_job_selthr, off_win_ratio, off_win_pts, off_hyp_true, off_hyp_filt, off_exact_list,
-      off_n_exact, off_counts, off_item_start, off_rtile_start, off_ctrl, off_partial, off_stats, total;
+      off_n_exact, off_counts, off_item_start, off_rtile_start, off_rtile_job, off_ctrl, off_partial, off_stats, total;
 };
 
 size_t bump(size_t& cur, size_t bytes) {
@@ -192,6 +192,7 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   L.off_counts = bump(cur, jvh * 4);
   L.off_item_start = bump(cur, (J + 1) * 4);
   L.off_rtile_start = bump(cur, (J + 1) * 4);
+  L.off_rtile_job = bump(cur, (size_t)d.max_rtiles * 4);
   L.off_ctrl = bump(cur, CTRL_WORDS * 4);
   L.off_partial = bump(cur, (size_t)d.max_rtiles * d.vn * 5 * 8);
   L.off_stats = bump(cur, 4 * 8);
@@ -222,6 +223,7 @@ WS make_ws(const Layout& L, void* base, bool stats) {
   w.counts = (int*)(b + L.off_counts);
   w.item_start = (int*)(b + L.off_item_start);
   w.rtile_start = (int*)(b + L.off_rtile_start);
+  w.rtile_job = (int*)(b + L.off_rtile_job);
   w.ctrl = (int*)(b + L.off_ctrl);
   w.partial = (double*)(b + L.off_partial);
   w.stats = stats ? (unsigned long long*)(b + L.off_stats) : nullptr;
@@ -682,9 +684,10 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   k_plan<<<1, 256, 0, st>>>(ws, d, 0);
   launches += 5;
   if (ld.filter) {
-    k_cc_init<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
-    k_cc_merge<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
-    k_cc_flatten<<<dim3((d.hw + 255) / 256, d.b), 256, 0, st>>>(lw, ld);
+    const int cgx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
+    k_cc_init<<<dim3(cgx, d.J), 256, 0, st>>>(ws, d, lw, ld);
+    k_cc_merge<<<dim3(cgx, d.J), 256, 0, st>>>(ws, d, lw, ld);
+    k_cc_flatten<<<dim3(cgx, d.J), 256, 0, st>>>(ws, d, lw, ld);
     k_cc_select<<<d.J, 256, 0, st>>>(lw, ld);
     launches += 4;
   }
@@ -767,15 +770,15 @@ extern "C" int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t ma
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t base_b = up((size_t)n * 2 * sizeof(float)), state_b = up((size_t)n * sizeof(int));
   const size_t part_b = may_sym ? up((size_t)n * tiles * sizeof(double)) : 0;
-  const size_t cloud_b = may_sym ? up((size_t)n * maxp * sizeof(double4)) : 0;
+  const size_t cloud_b = may_sym ? up((size_t)n * maxp * sizeof(float4)) : 0;
   int rc = ensure(&h->metric_mem, &h->metric_bytes, base_b + state_b + part_b + 2 * cloud_b);
   if (rc != CASA_OK) return rc;
   char* b = (char*)h->metric_mem;
   float* base = (float*)b;
   int* state = (int*)(b + base_b);
   double* partial = (double*)(b + base_b + state_b);
-  double4* cloud_gt = may_sym ? (double4*)(b + base_b + state_b + part_b) : nullptr;
-  double4* cloud_est = may_sym ? (double4*)(b + base_b + state_b + part_b + cloud_b) : nullptr;
+  float4* cloud_gt = may_sym ? (float4*)(b + base_b + state_b + part_b) : nullptr;
+  float4* cloud_est = may_sym ? (float4*)(b + base_b + state_b + part_b + cloud_b) : nullptr;
   k_pose_project<<<n, kMetricThreads, 0, st>>>(pp, poses, poses_gt, camera, model_points, model_counts, obj_model, valid,
                                                cloud_gt, cloud_est, base, state, out_rows);
   int launches = 1;

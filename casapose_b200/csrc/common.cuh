@@ -66,6 +66,7 @@ struct WS {
   int* counts;         // [J][vn][hn]
   int* item_start;     // [J+1]          exclusive prefix of scoring work items (chunks x vn) over active jobs
   int* rtile_start;    // [J+1]          exclusive prefix of refinement tiles over live jobs
+  int* rtile_job;      // [max_rtiles]   job of every refinement tile (written by k_plan in round 0)
   int* ctrl;           // [CTRL_WORDS]
   double* partial;     // [max_rtiles][vn][5]  per-tile sums nx*nx, nx*ny, ny*ny, nx*b, ny*b
   unsigned long long* stats;  // [4]

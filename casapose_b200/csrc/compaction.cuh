@@ -49,6 +49,9 @@ __global__ void __launch_bounds__(256) k_mask_bits(const float* __restrict__ mas
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        // seven of eight elements of a one-hot mask are +0: test the four bit patterns at once (-0 and NaN are
+        // non-zero patterns and take the per-element path below)
+        if (((__float_as_uint(f[0]) | __float_as_uint(f[1])) | (__float_as_uint(f[2]) | __float_as_uint(f[3]))) == 0u) continue;
         const int e0 = (i0 + u * 256 + tid) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -82,9 +85,11 @@ __global__ void __launch_bounds__(256) k_mask_bits(const float* __restrict__ mas
   for (int k = 0; k < 4; ++k) {
     const int p = p0 + k * 256 + tid;
     if (p < d.hw) ws.bits[(size_t)img * d.hw + p] = m[k];
-    for (int c = 0; c < d.oc; ++c) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (m[k] >> c) & 1u);
-      if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+    if (__any_sync(0xffffffffu, m[k] != 0u)) {
+      for (int c = 0; c < d.oc; ++c) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (m[k] >> c) & 1u);
+        if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+      }
     }
   }
   if (bad) atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_MASK_NOT_BINARY);
@@ -119,9 +124,11 @@ __global__ void __launch_bounds__(256) k_seg_bits(const float* __restrict__ seg,
       if (arg > 0) m = 1u << (arg - 1);
       ws.bits[(size_t)img * d.hw + p] = m;
     }
-    for (int c = 0; c < d.oc; ++c) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
-      if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+    if (__any_sync(0xffffffffu, m != 0u)) {
+      for (int c = 0; c < d.oc; ++c) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
+        if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+      }
     }
   }
   __syncthreads();
@@ -192,6 +199,10 @@ __global__ void __launch_bounds__(256) k_scatter(WS ws, Dims d) {
   const int img = blockIdx.y, tile = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int wcnt[32][32];  // [class][slot*8 + warp]
+  __shared__ int scnt[32];      // this tile's class counts
+  int mine = 0;
+  if (tid < d.oc) mine = scnt[tid] = ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile];
+  if (__syncthreads_or(mine) == 0) return;  // most tiles are pure background: nothing to scatter
   uint32_t m[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(256) k_scatter(WS ws, Dims d) {
     m[k] = p < d.hw ? ws.bits[(size_t)img * d.hw + p] : 0u;
   }
   for (int c = 0; c < d.oc; ++c) {
-    if (ws.tile_cnt[((size_t)img * d.oc + c) * d.nct + tile] == 0) continue;  // block-uniform
+    if (scnt[c] == 0) continue;  // block-uniform
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const unsigned bal = __ballot_sync(0xffffffffu, (m[k] >> c) & 1u);
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(256) k_scatter(WS ws, Dims d) {
   }
   __syncthreads();
   for (int c = warp; c < d.oc; c += 8) {
-    if (ws.tile_cnt[((size_t)img * d.oc + c) * d.nct + tile] == 0) continue;
+    if (scnt[c] == 0) continue;
     const int v = wcnt[c][lane];
     int x = v;
 #pragma unroll
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(256) k_scatter(WS ws, Dims d) {
   }
   __syncthreads();
   for (int c = 0; c < d.oc; ++c) {
-    if (ws.tile_cnt[((size_t)img * d.oc + c) * d.nct + tile] == 0) continue;
+    if (scnt[c] == 0) continue;
     const int job = img * d.oc + c;
     if (ws.job_flags[job] & JOB_OVERFLOW) continue;
     const int tbase = ws.tile_base[((size_t)img * d.oc + c) * d.nct + tile];

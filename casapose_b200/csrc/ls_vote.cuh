@@ -143,9 +143,11 @@ __global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ s
       ws.bits[(size_t)img * d.hw + p0 + q] = m;
       lw.cls9[(size_t)img * d.hw + p0 + q] = (unsigned char)c9;
     }
-    for (int c = 0; c < d.oc; ++c) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
-      if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+    if (__any_sync(0xffffffffu, m != 0u)) {
+      for (int c = 0; c < d.oc; ++c) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (m >> c) & 1u);
+        if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+      }
     }
   }
   __syncthreads();
@@ -186,58 +188,90 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-// Every pixel starts under the first pixel of its horizontal same-class run inside its warp's 32-pixel
-// segment (runs are pre-merged with ballots, no atomics); count and root list are reset.
-__global__ void __launch_bounds__(256) k_cc_init(LsWS lw, LsDims ld) {
-  const int img = blockIdx.y;
-  const int p = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
+// The three union-find passes walk the compacted pixel lists of the jobs (grid (gx, J), raster order inside a
+// list) instead of the whole image: only ~13 % of the pixels belong to any class.  A listed pixel is foreground
+// of its job's class c iff cls9 == c + 1 (every such pixel is listed: int(hot + 0.1) == 1 implies hot != 0).
+//
+// k_cc_init: every foreground pixel starts under the first pixel of its horizontal run inside its warp's 32 list
+// entries (runs are pre-merged with ballots, no atomics); its count is reset.
+__global__ void __launch_bounds__(256) k_cc_init(WS ws, Dims d, LsWS lw, LsDims ld) {
+  const int job = blockIdx.y, img = job / d.oc, c = job - img * d.oc;
+  const int lane = threadIdx.x & 31;
+  if (c == 0 && blockIdx.x == 0 && threadIdx.x == 0) lw.nroots[img] = 0;
+  const int tn = ws.job_tn[job];
+  const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
   const unsigned char* cls = lw.cls9 + (size_t)img * ld.hw;
-  const int c = p < ld.hw ? cls[p] : 0;
-  const int x = p % ld.w;
-  const int cl = __shfl_up_sync(0xffffffffu, c, 1);
-  const bool start = lane == 0 || x == 0 || cl != c;  // a run starts here
-  const unsigned sb = __ballot_sync(0xffffffffu, start);
-  if (p < ld.hw) {
+  for (int t0 = (blockIdx.x * 256 + threadIdx.x) & ~31; t0 < tn; t0 += gridDim.x * 256) {
+    const int t = t0 + lane;
+    uint32_t pk = 0xFFFFFFFFu;
+    int p = -1;
+    bool fg = false;
+    if (t < tn) {
+      pk = pix[t];
+      p = (int)(pk >> 16) * ld.w + (int)(pk & 0xFFFFu);
+      fg = cls[p] == c + 1;
+    }
+    const uint32_t pkl = __shfl_up_sync(0xffffffffu, pk, 1);
+    const bool fgl = __shfl_up_sync(0xffffffffu, fg ? 1 : 0, 1) != 0;
+    // the previous list entry is the left neighbour iff same row and x - 1 (packed values differ by one, x > 0)
+    const bool joined = lane > 0 && fg && fgl && (pk & 0xFFFFu) != 0u && pkl + 1u == pk;
+    const unsigned sb = __ballot_sync(0xffffffffu, !joined);
     const int sl = 31 - __clz(sb & (0xffffffffu >> (31 - lane)));  // nearest run start at or below this lane
-    lw.parent[(size_t)img * ld.hw + p] = p - (lane - sl);
-    lw.count[(size_t)img * ld.hw + p] = 0;
+    const int pstart = __shfl_sync(0xffffffffu, p, sl);
+    if (fg) {
+      lw.parent[(size_t)img * ld.hw + p] = pstart;
+      lw.count[(size_t)img * ld.hw + p] = 0;
+    }
   }
-  if (p == 0) lw.nroots[img] = 0;
 }
 
-// Unions only where they are not implied: the 32-pixel segment boundary, and the FIRST pixel of every
-// horizontal overlap with the row above (left and upper-left neighbours both of the class => implied).
-__global__ void __launch_bounds__(256) k_cc_merge(LsWS lw, LsDims ld) {
-  const int img = blockIdx.y;
-  const int p = blockIdx.x * 256 + threadIdx.x;
-  if (p >= ld.hw) return;
+// Unions only where they are not implied: at the first entry of a warp's 32 list entries, and at the FIRST pixel
+// of every horizontal overlap with the row above (left and upper-left neighbours both of the class => implied).
+__global__ void __launch_bounds__(256) k_cc_merge(WS ws, Dims d, LsWS lw, LsDims ld) {
+  const int job = blockIdx.y, img = job / d.oc, c = job - img * d.oc;
+  const int lane = threadIdx.x & 31;
+  const int tn = ws.job_tn[job];
+  const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
   const unsigned char* cls = lw.cls9 + (size_t)img * ld.hw;
   int* parent = lw.parent + (size_t)img * ld.hw;
-  const int c = cls[p];
-  if (c == 0) return;
-  const int y = p / ld.w, x = p - y * ld.w;
-  const bool left = x > 0 && cls[p - 1] == c;
-  if (left && (threadIdx.x & 31) == 0) uf_union(parent, p, p - 1);
-  if (y > 0 && cls[p - ld.w] == c) {
-    const bool upleft = x > 0 && cls[p - ld.w - 1] == c;
-    if (!(left && upleft)) uf_union(parent, p, p - ld.w);
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < tn; t += gridDim.x * 256) {
+    const uint32_t pk = pix[t];
+    const int x = pk & 0xFFFFu, y = pk >> 16, p = y * ld.w + x;
+    if (cls[p] != c + 1) continue;
+    const bool left = x > 0 && cls[p - 1] == c + 1;
+    if (left && lane == 0) uf_union(parent, p, p - 1);  // k_cc_init joined runs inside the 32 entries only
+    if (y > 0 && cls[p - ld.w] == c + 1) {
+      const bool upleft = x > 0 && cls[p - ld.w - 1] == c + 1;
+      if (!(left && upleft)) uf_union(parent, p, p - ld.w);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) k_cc_flatten(LsWS lw, LsDims ld) {
-  const int img = blockIdx.y;
-  const int p = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
-  const bool fg = p < ld.hw && lw.cls9[(size_t)img * ld.hw + p] != 0;
-  int r = -1;
-  if (fg) {
-    int* parent = lw.parent + (size_t)img * ld.hw;
-    r = uf_find(parent, p);
-    parent[p] = r;
-    if (r == p) lw.roots[(size_t)img * ld.hw + atomicAdd(&lw.nroots[img], 1)] = p;
+__global__ void __launch_bounds__(256) k_cc_flatten(WS ws, Dims d, LsWS lw, LsDims ld) {
+  const int job = blockIdx.y, img = job / d.oc, c = job - img * d.oc;
+  const int lane = threadIdx.x & 31;
+  const int tn = ws.job_tn[job];
+  const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
+  const unsigned char* cls = lw.cls9 + (size_t)img * ld.hw;
+  int* parent = lw.parent + (size_t)img * ld.hw;
+  for (int t0 = (blockIdx.x * 256 + threadIdx.x) & ~31; t0 < tn; t0 += gridDim.x * 256) {
+    const int t = t0 + lane;
+    int r = -1;
+    bool fg = false;
+    if (t < tn) {
+      const uint32_t pk = pix[t];
+      const int p = (int)(pk >> 16) * ld.w + (int)(pk & 0xFFFFu);
+      fg = cls[p] == c + 1;
+      if (fg) {
+        r = uf_find(parent, p);
+        parent[p] = r;
+        if (r == p) lw.roots[(size_t)img * ld.hw + atomicAdd(&lw.nroots[img], 1)] = p;
+      }
+    }
+    // component sizes: one atomic per distinct root in the warp (neighbouring pixels share their root)
+    const unsigned same = __match_any_sync(0xffffffffu, r);
+    if (fg && lane == __ffs(same) - 1) atomicAdd(&lw.count[(size_t)img * ld.hw + r], __popc(same));
   }
-  // component sizes: one atomic per distinct root in the warp (neighbouring pixels share their root)
-  const unsigned same = __match_any_sync(0xffffffffu, r);
-  if (fg && lane == __ffs(same) - 1) atomicAdd(&lw.count[(size_t)img * ld.hw + r], __popc(same));
 }
 
 // one block per (image, class): bincount -> threshold -> top_k -> pick index `which` (:64-76).
@@ -353,12 +387,7 @@ __global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDim
   __shared__ double sred[8][5];
   const float fh = (float)ld.h;
   for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
-    int lo = 0, hi = d.J;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (ws.rtile_start[mid] <= rt) lo = mid; else hi = mid;
-    }
-    const int job = lo, tile = rt - ws.rtile_start[job];
+    const int job = ws.rtile_job[rt], tile = rt - ws.rtile_start[job];
     const int tn = ws.job_tn[job];
     const int img = job / d.oc;
     const size_t base = (size_t)img * d.cap + ws.job_off[job];
@@ -520,12 +549,7 @@ __global__ void __launch_bounds__(256) k_ls_backward(WS ws, Dims d, LsWS lw, LsD
   __shared__ float sadj[32 * 6];
   const float fh = (float)ld.h;
   for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
-    int lo = 0, hi = d.J;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (ws.rtile_start[mid] <= rt) lo = mid; else hi = mid;
-    }
-    const int job = lo, tile = rt - ws.rtile_start[job];
+    const int job = ws.rtile_job[rt], tile = rt - ws.rtile_start[job];
     const int tn = ws.job_tn[job];
     const int img = job / d.oc;
     const size_t base = (size_t)img * d.cap + ws.job_off[job];

@@ -7,7 +7,7 @@
 // bit for bit; what is reproduced is its structure — a robust initial pose from point subsets, then the
 // Levenberg-Marquardt minimum of the reprojection error over all points, which is what the reference returns:
 //   * candidates: the full point set, every leave-one-out and every leave-two-out subset (46 for 9 points);
-//     each is solved by a normalised DLT (12x12 symmetric Jacobi eigen-solver), projected on SO(3) by a polar
+//     each is solved by a normalised DLT (reduced to a 4x4 symmetric eigen-problem), projected on SO(3) by a polar
 //     iteration and polished by 5 LM steps; the candidate with the most points inside 12 px (cv2's
 //     reprojectionError), then the smallest inlier cost, wins;
 //   * final: LM over all points from the winner, float64 throughout.
@@ -54,50 +54,65 @@ __device__ __forceinline__ void so3_exp(const double* w, double* E) {
   E[6] = -a * y + b * x * z;        E[7] = a * x + b * y * z;         E[8] = 1.0 - b * (x * x + y * y);
 }
 
-// smallest-eigenvalue eigenvector of the symmetric 12x12 matrix A (destroyed), cyclic Jacobi
-__device__ void jacobi12_smallest(double* A, double* V, double* vec) {
-  const int N = 12;
-  for (int i = 0; i < N * N; ++i) V[i] = 0.0;
-  for (int i = 0; i < N; ++i) V[i * N + i] = 1.0;
+// smallest-eigenvalue eigenvector of the symmetric 4x4 matrix A (destroyed), cyclic Jacobi
+__device__ __forceinline__ void jacobi4_smallest(double (&A)[4][4], double (&vec)[4]) {
+  double V[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) V[i][j] = i == j ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 30; ++sweep) {
     double off = 0.0, diag = 0.0;
-    for (int i = 0; i < N; ++i) {
-      diag += A[i * N + i] * A[i * N + i];
-      for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      diag += A[i][i] * A[i][i];
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
     }
     if (off <= 1e-30 * diag || off == 0.0) break;
-    for (int p = 0; p < N - 1; ++p)
-      for (int q = p + 1; q < N; ++q) {
-        const double apq = A[p * N + q];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {
+        const double apq = A[p][q];
         if (fabs(apq) < 1e-300) continue;
-        const double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
         const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < N; ++k) {  // columns p, q
-          const double akp = A[k * N + p], akq = A[k * N + q];
-          A[k * N + p] = c * akp - s * akq;
-          A[k * N + q] = s * akp + c * akq;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // columns p, q
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
         }
-        for (int k = 0; k < N; ++k) {  // rows p, q
-          const double apk = A[p * N + k], aqk = A[q * N + k];
-          A[p * N + k] = c * apk - s * aqk;
-          A[q * N + k] = s * apk + c * aqk;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // rows p, q
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
         }
-        for (int k = 0; k < N; ++k) {
-          const double vkp = V[k * N + p], vkq = V[k * N + q];
-          V[k * N + p] = c * vkp - s * vkq;
-          V[k * N + q] = s * vkp + c * vkq;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
         }
       }
   }
   int best = 0;
-  for (int i = 1; i < N; ++i)
-    if (A[i * N + i] < A[best * N + best]) best = i;
-  for (int k = 0; k < N; ++k) vec[k] = V[k * N + best];
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (A[i][i] < A[best][best]) best = i;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) vec[k] = best == 0 ? V[k][0] : best == 1 ? V[k][1] : best == 2 ? V[k][2] : V[k][3];
 }
 
-// normalised DLT on the points whose bit is set in `sel`; X [vn][3] object points, xn [vn][2] normalised image points
-__device__ bool pnp_dlt(const double* X, const double* xn, int vn, unsigned sel, double* R, double* t, double* A, double* V) {
+// normalised DLT on the points whose bit is set in `sel`; X [vn][3] object points, xn [vn][2] normalised image points.
+// The 12 unknowns (rows p1, p2, p3 of the 3x4 projection) are reduced to the last row: for fixed p3 the optimum is
+// p1 = S^-1 Sx p3, p2 = S^-1 Sy p3 with S = sum P P^T, Sx = sum x P P^T, Sy = sum y P P^T (P = normalised
+// homogeneous point), and p3 is the smallest eigenvector of the 4x4 Schur complement
+// M = sum (x^2 + y^2) P P^T - Sx S^-1 Sx - Sy S^-1 Sy.
+__device__ bool pnp_dlt(const double* X, const double* xn, int vn, unsigned sel, double* R, double* t) {
   double c[3] = {0, 0, 0};
   int m = 0;
   for (int i = 0; i < vn; ++i)
@@ -115,23 +130,105 @@ __device__ bool pnp_dlt(const double* X, const double* xn, int vn, unsigned sel,
     }
   if (!(ms > 0)) return false;
   const double s = 1.0 / sqrt(ms / m);
-  for (int i = 0; i < 144; ++i) A[i] = 0.0;
+  double S[4][4], Sx[4][4], Sy[4][4], Sq[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) S[a][b] = Sx[a][b] = Sy[a][b] = Sq[a][b] = 0.0;
   for (int i = 0; i < vn; ++i) {
     if (!((sel >> i) & 1u)) continue;
     const double P[4] = {(X[3 * i] - c[0]) * s, (X[3 * i + 1] - c[1]) * s, (X[3 * i + 2] - c[2]) * s, 1.0};
-    const double x = xn[2 * i], y = xn[2 * i + 1];
-    double r1[12], r2[12];
-    for (int k = 0; k < 4; ++k) {
-      r1[k] = P[k]; r1[4 + k] = 0.0; r1[8 + k] = -x * P[k];
-      r2[k] = 0.0;  r2[4 + k] = P[k]; r2[8 + k] = -y * P[k];
-    }
-    for (int a = 0; a < 12; ++a)
-      for (int b = a; b < 12; ++b) A[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
+    const double x = xn[2 * i], y = xn[2 * i + 1], q = x * x + y * y;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = a; b < 4; ++b) {
+        const double pp = P[a] * P[b];
+        S[a][b] += pp;
+        Sx[a][b] += x * pp;
+        Sy[a][b] += y * pp;
+        Sq[a][b] += q * pp;
+      }
   }
-  for (int a = 0; a < 12; ++a)
-    for (int b = 0; b < a; ++b) A[a * 12 + b] = A[b * 12 + a];
+#pragma unroll
+  for (int a = 1; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < a; ++b) {
+      S[a][b] = S[b][a]; Sx[a][b] = Sx[b][a]; Sy[a][b] = Sy[b][a]; Sq[a][b] = Sq[b][a];
+    }
+  // Cholesky S = L L^T (S is positive definite for non-coplanar points)
+  double L[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double d = S[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > 1e-14 * S[j][j])) return false;
+    L[j][j] = sqrt(d);
+#pragma unroll
+    for (int i = j + 1; i < 4; ++i) {
+      double v = S[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  // Tx = S^-1 Sx, Ty = S^-1 Sy (column by column), M = Sq - Sx Tx - Sy Ty
+  double Tx[4][4], Ty[4][4], M4[4][4];
+#pragma unroll
+  for (int col = 0; col < 4; ++col) {
+    double zx[4], zy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double vx = Sx[i][col], vy = Sy[i][col];
+#pragma unroll
+      for (int k = 0; k < i; ++k) {
+        vx -= L[i][k] * zx[k];
+        vy -= L[i][k] * zy[k];
+      }
+      zx[i] = vx / L[i][i];
+      zy[i] = vy / L[i][i];
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      double vx = zx[i], vy = zy[i];
+#pragma unroll
+      for (int k = i + 1; k < 4; ++k) {
+        vx -= L[k][i] * Tx[k][col];
+        vy -= L[k][i] * Ty[k][col];
+      }
+      Tx[i][col] = vx / L[i][i];
+      Ty[i][col] = vy / L[i][i];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double v = Sq[a][b];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v -= Sx[a][k] * Tx[k][b] + Sy[a][k] * Ty[k][b];
+      M4[a][b] = v;
+    }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) M4[a][b] = M4[b][a] = 0.5 * (M4[a][b] + M4[b][a]);
+  double p3[4];
+  jacobi4_smallest(M4, p3);
   double p[12];
-  jacobi12_smallest(A, V, p);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double v1 = 0, v2 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v1 += Tx[a][k] * p3[k];
+      v2 += Ty[a][k] * p3[k];
+    }
+    p[a] = v1;
+    p[4 + a] = v2;
+    p[8 + a] = p3[a];
+  }
   double M[9], p4[3];
   for (int r = 0; r < 3; ++r) {
     for (int k = 0; k < 3; ++k) M[3 * r + k] = p[4 * r + k] * s;
@@ -325,7 +422,6 @@ __global__ void __launch_bounds__(128) k_pnp(PnpParams pp, const float* __restri
   // candidates: 0 = all points, 1..vn = leave one out, then leave two out (a < b)
   const unsigned full = vn >= 32 ? 0xffffffffu : ((1u << vn) - 1u);
   const int ncand = 1 + vn + vn * (vn - 1) / 2;
-  double A[144], V[144];
   double bestR[9], bestT[3], bestCost = 1e300;
   int bestInl = -1, bestIdx = 0x7fffffff;
   for (int cnd = lane; cnd < ncand; cnd += 32) {
@@ -342,7 +438,7 @@ __global__ void __launch_bounds__(128) k_pnp(PnpParams pp, const float* __restri
       sel &= ~(1u << (a + 1 + k));
     }
     double R[9], t[3];
-    if (!pnp_dlt(X, xn, vn, sel, R, t, A, V)) continue;
+    if (!pnp_dlt(X, xn, vn, sel, R, t)) continue;
     pnp_lm(X, uv, vn, sel, K4, R, t, 5);
     int ninl = 0;
     double cost = 0;

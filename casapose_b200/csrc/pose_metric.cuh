@@ -5,12 +5,16 @@
 // serial tf.map_fn over (image, class): project the evaluation points with the estimated and the ground-truth
 // pose (project_tf, :173-182, float32), mean 2-D distance, mean 3-D distance (ADD) or — for the two symmetric
 // LINEMOD meshes, recognised by their vertex counts 7862 / 3417 (:618) — the mean closest-point distance
-// (ADD-S) taken from the float64 expansion |a|^2 - 2ab + |b|^2 over all N x N pairs (:596-610).
+// (ADD-S), which the reference takes from the float64 expansion |a|^2 - 2ab + |b|^2 over all N x N pairs
+// (:596-610).  Here the N x N search runs on the float32 points as the direct squared difference
+// (a-b).(a-b) — no cancellation, relative error 2e-7 of the squared distance, against the expansion's absolute
+// error of about 1e-10 mm^2: both far inside the 1e-5 relative tolerance of the parity test — because FP32 issues
+// four times faster than FP64 on this part.
 //
 //   k_pose_project  one block per object: guards, both projections, err_2d, ADD; symmetric objects leave their
-//                   two point clouds in scratch (float64 xyz + squared norm);
+//                   two point clouds (float32 xyz) in scratch;
 //   k_adds_min      (256-row tile, object): every thread owns one ground-truth point and scans the estimated
-//                   cloud through shared memory — FP64-FMA-bound, 5 flops per pair;
+//                   cloud through shared memory — FP32-issue-bound, 7 instructions per pair;
 //   k_pose_finalize sums the tile partials in order, applies the 0.1*diameter and 2-D thresholds.
 // Output rows are map_estimates' own: [err_2d, err_3d, valid_3d, valid_2d, missing, false_positive].
 #pragma once
@@ -64,8 +68,8 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {  // fixed or
 __global__ void __launch_bounds__(kMetricThreads)
     k_pose_project(PoseErrParams pp, const float* __restrict__ poses, const float* __restrict__ poses_gt,
                    const float* __restrict__ cam, const float* __restrict__ model_pts, const int* __restrict__ model_cnt,
-                   const int* __restrict__ obj_model, const int* __restrict__ valid, double4* __restrict__ cloud_gt,
-                   double4* __restrict__ cloud_est, float* __restrict__ base, int* __restrict__ state, float* __restrict__ out) {
+                   const int* __restrict__ obj_model, const int* __restrict__ valid, float4* __restrict__ cloud_gt,
+                   float4* __restrict__ cloud_est, float* __restrict__ base, int* __restrict__ state, float* __restrict__ out) {
   __shared__ double sh[kMetricThreads / 32];
   __shared__ float sRT[12], sGT[12], sK[9];
   const int obj = blockIdx.x;
@@ -102,9 +106,8 @@ __global__ void __launch_bounds__(kMetricThreads)
     const float dx = __fsub_rn(ug.x, ue.x), dy = __fsub_rn(ug.y, ue.y);
     e2 += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));  // tf.norm(axis=1), :591
     if (sym) {
-      const double ax = cg.x, ay = cg.y, az = cg.z, bx = ce.x, by = ce.y, bz = ce.z;
-      cloud_gt[(size_t)obj * pp.maxp + i] = make_double4(ax, ay, az, ax * ax + ay * ay + az * az);
-      cloud_est[(size_t)obj * pp.maxp + i] = make_double4(bx, by, bz, bx * bx + by * by + bz * bz);
+      cloud_gt[(size_t)obj * pp.maxp + i] = make_float4(cg.x, cg.y, cg.z, 0.f);
+      cloud_est[(size_t)obj * pp.maxp + i] = make_float4(ce.x, ce.y, ce.z, 0.f);
     } else {
       const float a = __fsub_rn(cg.x, ce.x), b = __fsub_rn(cg.y, ce.y), c = __fsub_rn(cg.z, ce.z);
       e3 += (double)__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));  // :621
@@ -122,9 +125,9 @@ __global__ void __launch_bounds__(kMetricThreads)
 // grid (tiles, n): rows = ground-truth points, scan = estimated points (adds_error(target, estimate), :619)
 __global__ void __launch_bounds__(kMetricThreads)
     k_adds_min(PoseErrParams pp, const int* __restrict__ model_cnt, const int* __restrict__ obj_model,
-               const int* __restrict__ state, const double4* __restrict__ cloud_gt, const double4* __restrict__ cloud_est,
+               const int* __restrict__ state, const float4* __restrict__ cloud_gt, const float4* __restrict__ cloud_est,
                double* __restrict__ partial) {
-  __shared__ double4 sB[kAddsTile];
+  __shared__ float4 sB[kAddsTile];
   __shared__ double sh[kMetricThreads / 32];
   const int obj = blockIdx.y;
   if (state[obj] != 2) return;
@@ -133,21 +136,30 @@ __global__ void __launch_bounds__(kMetricThreads)
   const int row0 = blockIdx.x * kMetricThreads;
   if (row0 >= cnt) return;
   const int r = row0 + threadIdx.x;
-  const double4 a = cloud_gt[(size_t)obj * pp.maxp + min(r, cnt - 1)];
-  const double4* B = cloud_est + (size_t)obj * pp.maxp;
-  double best = INFINITY;
+  const float4 a = cloud_gt[(size_t)obj * pp.maxp + min(r, cnt - 1)];
+  const float4* B = cloud_est + (size_t)obj * pp.maxp;
+  float best0 = INFINITY, best1 = INFINITY;  // two chains: the minimum is exact in any order
   for (int t0 = 0; t0 < cnt; t0 += kAddsTile) {
     const int nt = min(kAddsTile, cnt - t0);
     __syncthreads();
     for (int k = threadIdx.x; k < nt; k += kMetricThreads) sB[k] = B[t0 + k];
     __syncthreads();
+    int k = 0;
 #pragma unroll 4
-    for (int k = 0; k < nt; ++k) {
-      const double4 b = sB[k];
-      const double dot = a.x * b.x + a.y * b.y + a.z * b.z;
-      best = fmin(best, (a.w - 2.0 * dot) + b.w);  // row_norms_A - 2 A B^T + row_norms_B (:607)
+    for (; k + 1 < nt; k += 2) {
+      const float4 b0 = sB[k], b1 = sB[k + 1];
+      const float x0 = a.x - b0.x, y0 = a.y - b0.y, z0 = a.z - b0.z;
+      const float x1 = a.x - b1.x, y1 = a.y - b1.y, z1 = a.z - b1.z;
+      best0 = fminf(best0, fmaf(x0, x0, fmaf(y0, y0, z0 * z0)));
+      best1 = fminf(best1, fmaf(x1, x1, fmaf(y1, y1, z1 * z1)));
+    }
+    if (k < nt) {
+      const float4 b0 = sB[k];
+      const float x0 = a.x - b0.x, y0 = a.y - b0.y, z0 = a.z - b0.z;
+      best0 = fminf(best0, fmaf(x0, x0, fmaf(y0, y0, z0 * z0)));
     }
   }
+  const double best = (double)fminf(best0, best1);
   const double v = r < cnt ? (double)(float)sqrt(fabs(best) + 1e-5) : 0.0;  // :609, cast to float32 per point
   const double s = block_sum(v, sh);
   if (threadIdx.x == 0) partial[(size_t)obj * gridDim.x + blockIdx.x] = s;

@@ -128,7 +128,11 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
     const int ri = srun[0], rr = srun[1];
     if (job < d.J) {
       ws.item_start[job] = ri + wi + xi - ci;
-      if (rnd == 0) ws.rtile_start[job] = rr + wr + xr - cr;
+      if (rnd == 0) {
+        const int r0 = rr + wr + xr - cr;
+        ws.rtile_start[job] = r0;
+        for (int k = 0; k < cr; ++k) ws.rtile_job[r0 + k] = job;
+      }
     }
     __syncthreads();
     if (tid == (int)blockDim.x - 1) {
@@ -480,12 +484,7 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc) 
   const int n_rtiles = ws.rtile_start[d.J];
   __shared__ double sred[8][5];
   for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
-  int lo = 0, hi = d.J;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (ws.rtile_start[mid] <= rt) lo = mid; else hi = mid;
-  }
-  const int job = lo, tile = rt - ws.rtile_start[job];
+  const int job = ws.rtile_job[rt], tile = rt - ws.rtile_start[job];
   const int tn = ws.job_tn[job];
   const int img = job / d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];

@@ -26,12 +26,18 @@ def dlt(X, xn):
     c = X.mean(0)
     s = 1.0 / np.sqrt(((X - c) ** 2).sum(1).mean())
     Xs = (X - c) * s
-    A = np.zeros((2 * len(X), 12))
-    for i, (P, (x, y)) in enumerate(zip(Xs, xn)):
-        A[2 * i, 0:3], A[2 * i, 3], A[2 * i, 8:11], A[2 * i, 11] = P, 1, -x * P, -x
-        A[2 * i + 1, 4:7], A[2 * i + 1, 7], A[2 * i + 1, 8:11], A[2 * i + 1, 11] = P, 1, -y * P, -y
-    _, v = np.linalg.eigh(A.T @ A)
-    p = v[:, 0].reshape(3, 4)
+    P = np.concatenate([Xs, np.ones((len(X), 1))], 1)  # [m,4]
+    x, y = xn[:, 0], xn[:, 1]
+    PP = P[:, :, None] * P[:, None, :]
+    S, Sx, Sy = PP.sum(0), (x[:, None, None] * PP).sum(0), (y[:, None, None] * PP).sum(0)
+    Sq = ((x * x + y * y)[:, None, None] * PP).sum(0)
+    np.linalg.cholesky(S)  # positive definite for non-coplanar points (LinAlgError otherwise)
+    Tx, Ty = np.linalg.solve(S, Sx), np.linalg.solve(S, Sy)
+    M4 = Sq - Sx @ Tx - Sy @ Ty  # Schur complement on the last row of the projection
+    M4 = 0.5 * (M4 + M4.T)
+    _, v = np.linalg.eigh(M4)
+    p3 = v[:, 0]
+    p = np.stack([Tx @ p3, Ty @ p3, p3])
     M = p[:, :3] * s
     p4 = p[:, 3] - M @ c
     if np.linalg.det(M) < 0:

@@ -673,46 +673,42 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
 
   CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
+  // the launch list: replayed as a CUDA graph (kernel parameters patched per call) unless debug outputs are asked for
+  std::vector<Step> steps;
+  steps.reserve(16);
   {
     const size_t sm = (size_t)kCountTile * ld.nc * 4;
     if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_ls_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_ls_classify<<<dim3(d.nct, d.b), 256, sm, st>>>(seg, ws, d, lw, ld);
+    steps.push_back(kstep((const void*)k_ls_classify, dim3(d.nct, d.b), 256, sm).arg(seg).arg(ws).arg(d).arg(lw).arg(ld));
   }
-  k_scan_tiles<<<d.J, 128, 0, st>>>(ws, d);
-  k_job_table<<<(d.b + 63) / 64, 64, 0, st>>>(ws, d);
-  k_scatter<<<dim3(d.nct, d.b), 256, 0, st>>>(ws, d);
-  k_plan<<<1, 256, 0, st>>>(ws, d, 0);
-  launches += 5;
+  steps.push_back(kstep((const void*)k_scan_tiles, d.J, 128).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_job_table, (d.b + 63) / 64, 64).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_plan, 1, 256).arg(ws).arg(d).arg((int)0));
+  const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
   if (ld.filter) {
-    const int cgx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
-    k_cc_init<<<dim3(cgx, d.J), 256, 0, st>>>(ws, d, lw, ld);
-    k_cc_merge<<<dim3(cgx, d.J), 256, 0, st>>>(ws, d, lw, ld);
-    k_cc_flatten<<<dim3(cgx, d.J), 256, 0, st>>>(ws, d, lw, ld);
-    k_cc_select<<<d.J, 256, 0, st>>>(lw, ld);
-    launches += 4;
+    steps.push_back(kstep((const void*)k_cc_init, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld));
+    steps.push_back(kstep((const void*)k_cc_merge, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld));
+    steps.push_back(kstep((const void*)k_cc_flatten, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld));
+    steps.push_back(kstep((const void*)k_cc_select, d.J, 256).arg(lw).arg(ld));
   }
   const int grid_x = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
-  {
-    const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
-    if (d.vn == 9)
-      k_gather_dirs<18><<<dim3(gx, d.J), 256, 0, st>>>(direct, ws, d);
-    else
-      k_gather_dirs<0><<<dim3(gx, d.J), 256, 0, st>>>(direct, ws, d);
-    k_ls_weights<<<dim3(gx, d.J), 256, 0, st>>>(ws, d, lw, ld, seg, conf);
-    launches += 2;
-  }
-  k_ls_reduce<<<dim3(grid_x, d.vn), 256, 0, st>>>(ws, d, lw, ld);
+  steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gx, d.J), 256)
+                      .arg(direct).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_ls_weights, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(conf));
+  steps.push_back(kstep((const void*)k_ls_reduce, dim3(grid_x, d.vn), 256).arg(ws).arg(d).arg(lw).arg(ld));
   if (!out_points) out_points = (float*)(base + off_tmp_out);
-  k_ls_solve<<<d.J, 32, 0, st>>>(ws, d, ld, out_points, dbg.sums);
-  launches += 2;
+  steps.push_back(kstep((const void*)k_ls_solve, d.J, 32).arg(ws).arg(d).arg(ld).arg(out_points).arg(dbg.sums));
   if (grad) {
     float* adj = (float*)(base + off_adj);
     CUDA_TRY(cudaMemsetAsync(grad->grad_direct, 0, npx * 2 * d.vn * sizeof(float), st));
     CUDA_TRY(cudaMemsetAsync(grad->grad_conf, 0, npx * d.vn * sizeof(float), st));
-    k_ls_adjoint<<<d.J, 32, 0, st>>>(ws, d, ld, grad->grad_points, adj);
-    k_ls_backward<<<grid_x, 256, 0, st>>>(ws, d, lw, ld, adj, grad->grad_direct, grad->grad_conf);
-    launches += 2;
+    steps.push_back(kstep((const void*)k_ls_adjoint, d.J, 32).arg(ws).arg(d).arg(ld).arg(grad->grad_points).arg(adj));
+    steps.push_back(kstep((const void*)k_ls_backward, grid_x, 256).arg(ws).arg(d).arg(lw).arg(ld).arg(adj).arg(grad->grad_direct).arg(grad->grad_conf));
   }
+  launches = (int64_t)steps.size();
+  rc = (h->use_graph && !debug) ? run_graph(h, steps, ws, st) : run_direct(h, steps, ws, st);
+  if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
   if (dbg.labels) CUDA_TRY(cudaMemcpyAsync(dbg.labels, lw.cls9, npx, cudaMemcpyDeviceToDevice, st));
   if (dbg.parent && ld.filter) CUDA_TRY(cudaMemcpyAsync(dbg.parent, lw.parent, npx * 4, cudaMemcpyDeviceToDevice, st));

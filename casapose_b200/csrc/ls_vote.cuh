@@ -299,16 +299,39 @@ __global__ void __launch_bounds__(256) k_cc_select(LsWS lw, LsDims ld) {
         key = t;
       }
   }
-  __shared__ unsigned long long stop[256 * 3];
-  __shared__ int snp[256], snc[256];
-  for (int k = 0; k < 3; ++k) stop[tid * 3 + k] = top[k];
-  snp[tid] = npix;
-  snc[tid] = ncomp;
+  // merge the per-thread top-3 lists: shuffle tree inside each warp, then thread 0 over the 8 warp results
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long other[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) other[k] = __shfl_down_sync(0xffffffffu, top[k], o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      unsigned long long key = other[k];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (key > top[j]) {
+          const unsigned long long t = top[j];
+          top[j] = key;
+          key = t;
+        }
+    }
+  }
+  npix = __reduce_add_sync(0xffffffffu, npix);
+  ncomp = __reduce_add_sync(0xffffffffu, ncomp);
+  __shared__ unsigned long long stop[8 * 3];
+  __shared__ int snp[8], snc[8];
+  if (lane == 0) {
+    for (int k = 0; k < 3; ++k) stop[warp * 3 + k] = top[k];
+    snp[warp] = npix;
+    snc[warp] = ncomp;
+  }
   __syncthreads();
   if (tid == 0) {
     unsigned long long best[3] = {0ull, 0ull, 0ull};
     int tp = 0, tc = 0;
-    for (int i = 0; i < 256; ++i) {
+    for (int i = 0; i < 8; ++i) {
       tp += snp[i];
       tc += snc[i];
       for (int k = 0; k < 3; ++k) {

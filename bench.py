@@ -276,11 +276,30 @@ def main():
         def wait(self):
             return self.v
 
+    # The gather is a replayed CUDA graph (sharding.GraphGather): the eager collective costs the host ~75 us per
+    # step, which the host-latency-bound loop cannot hide.  CASA_BENCH_EAGER_GATHER=1 selects the eager path.
+    ggather = None
+    if distributed and not os.environ.get("CASA_BENCH_EAGER_GATHER"):
+        try:
+            ggather = sharding.GraphGather((B, OC, VN, 2), dev, world, side)
+        except Exception as exc:  # capture unsupported by this NCCL / torch build: keep the eager path
+            if rank == 0:
+                print("[bench] graph gather unavailable (%s); using the eager all-gather" % exc, file=sys.stderr)
+            ggather = None
+    start_img, _ = sharding.shard_bounds(world * B, rank, world)  # this rank's B images of the global batch
+    counter = [0]
+
     def step(seed):
-        start, _ = sharding.shard_bounds(world * B, rank, world)  # this rank's B images of the global batch
-        local = ransac_voting_layer_all_masks(mask, vertex, HN, seed=seed, image_offset=start)
         if not distributed:
-            return _Done(local)
+            return _Done(ransac_voting_layer_all_masks(mask, vertex, HN, seed=seed, image_offset=start_img))
+        i = counter[0]
+        counter[0] += 1
+        if ggather is not None:
+            ransac_voting_layer_all_masks(mask, vertex, HN, seed=seed, image_offset=start_img, out=ggather.buffer(i))
+            ev = torch.cuda.Event()
+            ev.record()
+            return ggather.launch(i, ev)
+        local = ransac_voting_layer_all_masks(mask, vertex, HN, seed=seed, image_offset=start_img)
         ev = torch.cuda.Event()
         ev.record()
         return sharding.gather_points_async(local, world * B, stream=side, after=ev)
@@ -322,12 +341,22 @@ def main():
         launches += nl.value
         units += st[0]
         exact_units += st[1]
-    pending.wait()
+    gathered = pending.wait()
     e1.record()
     barrier()
     clocks = sampler.stop()
     _lib.check(lib.casa_set_timing(hdl, 0))
     elapsed_ms = e0.elapsed_time(e1)
+    gather_ok = None
+    if distributed:  # the gathered keypoints of the last step: this rank's rows are its own result, every row finite
+        mine = ggather.inp[(counter[0] - 1) % len(ggather.inp)] if ggather is not None else None
+        own = gathered[start_img:start_img + B]
+        ok = bool(torch.isfinite(gathered).all()) and tuple(gathered.shape) == (world * B, OC, VN, 2)
+        if mine is not None:
+            ok = ok and bool(torch.equal(own, mine))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
     if distributed:
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -362,7 +391,8 @@ def main():
                 "variant": args.variant, "masked_pixels_per_frame": sum_tn / B,
                 "units_per_step": units / max(args.steps, 1), "flop_per_unit": FLOP_PER_UNIT,
                 "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush needed" % (in_bytes / 1e6),
-                "parallelism": "images sharded across ranks (same seeded frames on every rank, distinct global image indices), async NCCL all-gather of [b,8,9,2] keypoints" if distributed else "single GPU",
+                "parallelism": "images sharded across ranks (same seeded frames on every rank, distinct global image indices), NCCL all-gather of [b,8,9,2] keypoints on a side stream (%s), gathered result verified: %s" % (
+                    "replayed CUDA graph" if ggather is not None else "eager", gather_ok) if distributed else "single GPU",
                 "exact_fallback_fraction": exact_units / units if units else None,
             },
             "clocks": clocks,
@@ -387,6 +417,14 @@ def main():
             }
         print(json.dumps(line))
     if distributed:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if ggather is not None:
+            # A process group whose collectives were captured into CUDA graphs does not tear down reliably
+            # (destroy_process_group blocked for minutes in testing); every collective of this run has completed,
+            # so the rank leaves without communicator teardown.
+            torch.cuda.synchronize()
+            os._exit(0)
         dist.barrier()
         dist.destroy_process_group()
 

@@ -43,6 +43,7 @@ def ransac_voting_layer_all_masks(
     pix_capacity=0,
     force_exact=False,
     seg_scores=False,
+    out=None,
 ):
     """
     :param mask:      [b,h,w,oc]   float32 {0,1}
@@ -51,6 +52,7 @@ def ransac_voting_layer_all_masks(
     :param vertex:    [b,h,w,vn,2] float32 (dy,dx)   (a [b,h,w,vn*2] tensor is viewed as such;
                       [b,h,w,oc,vn,2] = one field per class, pose_evaluation.py:38-45)
     :param round_hyp_num: hypotheses per round
+    :param out:       optional preallocated [b,oc,vn,2] float32 result tensor on the inputs' device
     :return: [b,oc,vn,2] float32 (x,y) — and a dict of intermediates if return_debug
     """
     mask = as_cuda_f32(mask, "mask")
@@ -85,7 +87,12 @@ def ransac_voting_layer_all_masks(
         selection = as_cuda_f32(selection, "selection")
         if tuple(selection.shape) != (b, oc, h, w):
             raise ValueError("selection must be [b,oc,h,w]")
-    out = torch.empty((b, oc, vn, 2), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((b, oc, vn, 2), dtype=torch.float32, device=dev)
+    else:
+        out = as_cuda_f32(out, "out")
+        if tuple(out.shape) != (b, oc, vn, 2) or out.device != dev:
+            raise ValueError("out must be [b,oc,vn,2] = %s on %s" % ((b, oc, vn, 2), dev))
     dbg_struct = None
     dbg = None
     if return_debug:

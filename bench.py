@@ -182,6 +182,9 @@ def run_ls(args):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
+    nl = C.c_int64()
+    _lib.check(_lib.lib().casa_last_launches(_lib.handle(0), C.byref(nl)))
+    fwd_launches = int(nl.value)
     # backward (casa_ls_vote_backward: forward recomputation + adjoint + one pass over the listed pixels + zero fill)
     gout = torch.randn((B, OC, VN, 2), device="cuda")
     for _ in range(3):
@@ -212,11 +215,11 @@ def run_ls(args):
         "data": "synthetic", "config": {"workload": "config 1 shape: [b,480,640,9+18+9] network-output split -> CoordLSVotingWeighted(filter_estimates=True), batch %d" % B,
                                         "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (alg_bytes / 1e6)},
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "CoordLSVotingWeighted (k_ls_classify .. k_ls_solve, 12 launches)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "CoordLSVotingWeighted (k_ls_classify .. k_ls_solve, %d launches replayed as one CUDA graph)" % fwd_launches, "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src},
         "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
                          "sample": "numpy oracle, 1 frame, %.2f s" % cpu_s},
-        "gpu_launches": 12 * args.steps,
+        "gpu_launches": fwd_launches * args.steps,
         "backward": {"ms_per_step": bwd_ms, "frames_per_s": B / (bwd_ms * 1e-3),
                      "note": "forward recomputation + gradients w.r.t. direct and confidence logits (dense, zero-filled)",
                      "bytes_written": B * H * W * 4 * 3 * VN},

@@ -91,7 +91,7 @@ __device__ __forceinline__ float hot_of_row(const float* row, int nc, int cls) {
 
 // same tiling and outputs as k_mask_bits (compaction.cuh), fed by the segmentation logits: the tile's
 // [1024 x nc] floats are staged in shared memory with coalesced loads, then every thread classifies 4 pixels
-extern __shared__ float ls_smem[];
+extern __shared__ __align__(16) float ls_smem[];
 __global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ seg, WS ws, Dims d, LsWS lw, LsDims ld) {
   const int img = blockIdx.y, tile = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -101,7 +101,13 @@ __global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ s
   const int npx = min(kCountTile, d.hw - p0);
   const float* slab = seg + ((size_t)img * d.hw + p0) * ld.nc;
   const int nfl = npx * ld.nc;
-  for (int i = tid; i < nfl; i += 256) ls_smem[i] = __ldg(slab + i);
+  if (((nfl | (int)(((size_t)img * d.hw + p0) * ld.nc)) & 3) == 0 && (reinterpret_cast<uintptr_t>(seg) & 15) == 0) {
+    const float4* slab4 = reinterpret_cast<const float4*>(slab);  // 16-byte aligned slab: 128-bit loads
+    float4* sm4 = reinterpret_cast<float4*>(ls_smem);
+    for (int i = tid; i < nfl / 4; i += 256) sm4[i] = __ldg(slab4 + i);
+  } else {
+    for (int i = tid; i < nfl; i += 256) ls_smem[i] = __ldg(slab + i);
+  }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -419,19 +425,30 @@ __global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDim
     const float2* vd = ws.vdir + base * d.vn + (size_t)v * tn;
     const float* cc = lw.cconf + base * d.vn + (size_t)v * tn;
     double s[5] = {0, 0, 0, 0, 0};
+    // phase 1: all loads of the thread's 4 pixels in flight together; phase 2: arithmetic
+    float lw_[kRefineTile / 256], lc_[kRefineTile / 256];
+    uint32_t lp_[kRefineTile / 256];
+    float2 ld_[kRefineTile / 256];
 #pragma unroll
     for (int k = 0; k < kRefineTile / 256; ++k) {
       const int t = tile * kRefineTile + k * 256 + tid;
-      if (t >= tn) continue;
-      const float w = wt[t];
-      if (w == 0.f) continue;  // multiply_no_nan (:107-108)
-      const uint32_t pk = pix[t];
+      const bool in = t < tn;
+      lw_[k] = in ? wt[t] : 0.f;
+      lp_[k] = in ? pix[t] : 0u;
+      ld_[k] = in ? __ldg(vd + t) : make_float2(0.f, 0.f);  // (n0, n1) = (dy, dx)
+      lc_[k] = in ? cc[t] : 0.f;  // (entries with weight 0 hold stale values: never used)
+    }
+#pragma unroll
+    for (int k = 0; k < kRefineTile / 256; ++k) {
+      const float w = lw_[k];
+      if (w == 0.f) continue;  // multiply_no_nan (:107-108); also positions past the end of the list
+      const uint32_t pk = lp_[k];
       const int x = pk & 0xFFFFu, y = pk >> 16;
-      const float2 dv = __ldg(vd + t);  // (n0, n1) = (dy, dx)
+      const float2 dv = ld_[k];
       const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dv.x, dv.x), __fmul_rn(dv.y, dv.y)));  // :89
       const float n0 = nrm != 0.f ? __fdiv_rn(dv.x, nrm) : 0.f;  // divide_no_nan :90
       const float n1 = nrm != 0.f ? __fdiv_rn(dv.y, nrm) : 0.f;
-      const float wc = cc[t];
+      const float wc = lc_[k];
       const float r00 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n0, n0)), wc);  // :92-94
       const float r01 = __fmul_rn(__fsub_rn(0.0f, __fmul_rn(n0, n1)), wc);
       const float r11 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n1, n1)), wc);

@@ -491,13 +491,22 @@ __global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc) 
   const float2* vd = job_dirs(ws, d, img, job, tn, v);
   const float2 wp = ws.win_pts[job * d.vn + v];
   double s[5] = {0, 0, 0, 0, 0};
+  // phase 1: all loads of the thread's 4 pixels in flight together; phase 2: arithmetic
+  uint32_t lp_[kRefineTile / 256];
+  float2 ld_[kRefineTile / 256];
+#pragma unroll
+  for (int k = 0; k < kRefineTile / 256; ++k) {
+    const int t = tile * kRefineTile + k * 256 + tid;
+    lp_[k] = t < tn ? pix[t] : 0u;
+    ld_[k] = t < tn ? load_dir(vd, t) : make_float2(0.f, 0.f);
+  }
 #pragma unroll
   for (int k = 0; k < kRefineTile / 256; ++k) {
     const int t = tile * kRefineTile + k * 256 + tid;
     if (t < tn) {
-      const uint32_t pk = pix[t];
+      const uint32_t pk = lp_[k];
       const int x = pk & 0xFFFFu, y = pk >> 16;
-      const float2 dv = load_dir(vd, t);
+      const float2 dv = ld_[k];
       const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
       const bool in = exact_inlier(wp.x, wp.y, cx, cy, dv.x, dv.y, exact_norm(dv.x, dv.y), fc.thr);  // :353
       const bool finite = fabsf(dv.x) <= 3.0e38f && fabsf(dv.y) <= 3.0e38f;

@@ -20,6 +20,27 @@ host = ransac_voting_layer_all_masks_host(torch.from_numpy(d["mask"]).pin_memory
 layer = CoordLSVotingWeighted("ls", 4, num_points=9, filter_estimates=True)
 ls = layer([torch.from_numpy(d["seg_logits"]).cuda(), torch.from_numpy(d["vertex"].reshape(2, 96, 128, 18)).cuda(),
             torch.from_numpy(d["conf_logits"]).cuda()])
+# section-8(f) kernels: LS backward, batched PnP, ADD / ADD-S (one model with the symmetric meshes' vertex count)
+from casapose_b200.pose_estimation.ransac_voting import pnp_cuda, pose_errors_cuda  # noqa: E402
+
+seg_t = torch.from_numpy(d["seg_logits"]).cuda()
+dir_t = torch.from_numpy(d["vertex"].reshape(2, 96, 128, 18)).cuda()
+conf_t = torch.from_numpy(d["conf_logits"]).cuda()
+gd, gw = layer.backward([seg_t, dir_t, conf_t], torch.randn((2, 3, 9, 2), device="cuda"))
+ls_plain = CoordLSVotingWeighted("ls2", 4, num_points=9, sigmoid_weights=True)([seg_t, dir_t, conf_t])
+rng = np.random.default_rng(0)
+K = synthetic.camera_matrix(96).astype(np.float32)
+kp3 = d["keypoints_3d"].astype(np.float32)  # [oc,9,3]
+RT = d["poses_gt"][0].astype(np.float32)    # [oc,3,4]
+cam = kp3 @ RT[:, :, :3].transpose(0, 2, 1) + RT[:, None, :, 3]
+uv = cam @ K.T
+uv = (uv[..., :2] / uv[..., 2:]).astype(np.float32) + rng.normal(scale=0.5, size=(3, 9, 2)).astype(np.float32)
+cams = np.broadcast_to(K, (3, 3, 3)).copy()
+poses = pnp_cuda(torch.from_numpy(uv).cuda(), kp3, cams, np.tile(np.array([0, 0, 0, 0, 0, 0, 0, 1, 128, 96], np.float32), (3, 1)))
+counts = np.array([700, 3417, 9], np.int32)
+pts = (rng.uniform(-0.5, 0.5, size=(3, 3417, 3)) * 80).astype(np.float32)
+rows = pose_errors_cuda(poses, RT, cams, pts, counts, np.full(3, 100.0, np.float32), np.array([1, 1, 0], np.int32), 5.0)
 torch.cuda.synchronize()
+assert torch.isfinite(gd).all() and torch.isfinite(gw).all() and torch.isfinite(rows).all() and torch.isfinite(ls_plain).all()
 assert torch.equal(out.cpu(), host)
 print("sanitize run ok", float(out.abs().sum()), float(ls.abs().sum()))

@@ -131,6 +131,16 @@ def test_graph_replay_equals_debug_path_and_oracle(vote, variant):
     assert torch.equal(shifted[5:], part)
 
 
+@pytest.mark.parametrize("vn,hn,ids", [(5, 100, (1,)), (12, 33, (1, 5)), (1, 300, (5, 6, 8))])
+def test_other_shapes_keypoint_counts_and_ragged_hypothesis_numbers(vote, vn, hn, ids):
+    """vn != 9 (generic direction gather), hypothesis counts that are not a multiple of the 256-wide groups,
+    a single class: still bit-exact against the oracle."""
+    d = synthetic.make_frames(2, 96, 128, ids, variant="hard")
+    v9 = d["vertex"]
+    vertex = np.ascontiguousarray(np.concatenate([v9, v9[:, :, :, ::-1]], axis=3)[:, :, :, :vn])  # up to 18 keypoint fields
+    _compare(vote, d["mask"], vertex, hn, seed=3, max_iter=4)
+
+
 def test_degenerate_inputs(vote):
     h, w = 64, 80
     mask = np.zeros((1, h, w, 4), np.float32)

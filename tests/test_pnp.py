@@ -104,3 +104,27 @@ def test_pipeline_with_gpu_pnp_gives_identical_add_verdicts(cuda_lib):
     assert torch.equal(k_cv, k_gpu)
     assert np.array_equal(s_cv[1], s_gpu[1]) and np.array_equal(s_cv[0], s_gpu[0])  # valid_3d (ADD) and valid_2d
     assert np.abs(p_cv.numpy()[..., 3] - p_gpu.numpy()[..., 3]).max() < 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vn", [6, 12, 16])
+def test_gpu_pnp_other_keypoint_counts(cuda_lib, vn):
+    import torch
+
+    from casapose_b200.pose_estimation.ransac_voting import pnp_cuda
+
+    rng = np.random.default_rng(vn)
+    K = synthetic.camera_matrix(480).astype(F)
+    n = 12
+    X = (rng.uniform(-0.5, 0.5, size=(n, vn, 3)) * 150).astype(F)
+    p2 = np.zeros((n, vn, 2), F)
+    for i in range(n):
+        R = synthetic._random_rotation(rng)
+        t = np.array([rng.uniform(-150, 150), rng.uniform(-100, 100), rng.uniform(600, 1200)])
+        cam = X[i] @ R.T + t
+        uv = cam @ K.T
+        p2[i] = (uv[:, :2] / uv[:, 2:]).astype(F) + rng.normal(scale=0.3, size=(vn, 2)).astype(F)
+    got = pnp_cuda(torch.from_numpy(p2).cuda(), X, np.broadcast_to(K, (n, 3, 3)).copy()).cpu().numpy()
+    for i in range(n):
+        ref = pnp_np.pnp(X[i], p2[i], K)
+        assert np.abs(got[i] - ref).max() < 1e-3, (vn, i)

@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=None,
                     help="frames of the batch the CPU restatement is timed on (default: 8 for the cpu_baseline leg = about 8 s, 1 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="ransac", choices=["ransac", "ls"],
+    ap.add_argument("--workload", default="ransac", choices=["ransac", "ls", "pose"],
                     help="ransac: BASELINE config 2 (the headline); ls: CoordLSVotingWeighted on config-1-shaped tensors")
     return ap.parse_args()
 
@@ -226,10 +226,67 @@ def run_ls(args):
     }))
 
 
+def run_pose(args):
+    """Secondary line: the whole post-network evaluation of a batch (SURVEY.md 8a rows A1-C3 with the 8f rows on the
+    GPU): seg arg-max -> voting -> batched PnP -> ADD, device-resident (DeviceEvaluator), one [oc,8] read-back per
+    batch inside the timed region; beside it the drop-in with the reference's own host stages (OpenCV PnP, numpy
+    metrics) on the same inputs."""
+    import numpy as np
+    import torch
+
+    from casapose_b200 import _lib, synthetic
+    from casapose_b200.pose_estimation import DeviceEvaluator, estimate_and_evaluate_poses
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device")
+    if _lib._sources_newer_than_lib():
+        _lib.build()
+    B = args.batch
+    d = synthetic.make_frames(B, H, W, synthetic.CONFIG_8_IDS, variant=args.variant, with_logits=True)
+    seg = torch.from_numpy(d["seg_logits"]).cuda()
+    tgt = torch.from_numpy(np.concatenate([(d["labels"] == 0)[..., None].astype(np.float32), d["mask"]], axis=-1)).cuda()
+    vert = torch.from_numpy(d["vertex"].reshape(B, H, W, 2 * VN)).cuda()
+    K = synthetic.camera_matrix(H).astype(np.float32)
+    offsets = np.zeros((B, 10), np.float32)
+    offsets[:, 7], offsets[:, 8], offsets[:, 9] = 1.0, W, H
+    gt = d["poses_gt"].astype(np.float32)
+    ev = DeviceEvaluator(d["keypoints_3d"], K, d["diameters"])
+    for it in range(max(args.warmup, 3)):
+        ev(seg, tgt, vert, gt, offsets, seed=it)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        stats, _, _ = ev(seg, tgt, vert, gt, offsets, seed=100 + it)  # ends with the [oc,8] read-back: host-visible result
+    dt = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    kp3 = np.broadcast_to(d["keypoints_3d"][None, :, None], (B, OC, 1, VN, 3)).copy()
+    cams = np.broadcast_to(K, (B, 3, 3)).copy()
+    diam = np.broadcast_to(d["diameters"][None], (B, OC)).copy()
+    n_host = 3
+    t0 = time.perf_counter()
+    for it in range(n_host):
+        s_host, _, _ = estimate_and_evaluate_poses(seg, tgt, vert, gt[:, :, None], kp3, cams, diam, offsets, seed=100 + it)
+    dt_host = (time.perf_counter() - t0) / n_host
+    print(json.dumps({
+        "metric": "post-network pose evaluation frames/s (480x640, 8 obj x 9 kp: voting + PnP + ADD)", "value": B / dt,
+        "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 voting, f64 PnP", "data": "synthetic",
+        "config": {"workload": "batch %d: seg logits [b,480,640,9] + vector field -> casa_ransac_vote_seg -> casa_pnp -> casa_pose_errors, wall clock incl. the per-batch read-back" % B},
+        "clocks": clocks,
+        "host_stages": {"value": B / dt_host, "unit": "frames/s", "ms_per_step": dt_host * 1e3,
+                        "note": "same voting kernels, then OpenCV solvePnPRansac + solvePnP and numpy metrics on the host like the reference (drop-in defaults), %d batches" % n_host},
+        "valid_3d": [float(x) for x in stats["valid_3d"]], "valid_3d_host_stages": [float(x) for x in np.atleast_1d(s_host[1])],
+    }))
+
+
 def main():
     args = parse()
     if args.workload == "ls":
         return run_ls(args)
+    if args.workload == "pose":
+        return run_pose(args)
     if args.impl == "reference":
         return run_reference(args)
 

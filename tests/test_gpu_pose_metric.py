@@ -102,3 +102,23 @@ def test_pipeline_with_gpu_metrics_gives_identical_statistics(cuda_lib):
     for k in (0, 1, 2, 3, 6, 7):
         assert np.array_equal(np.asarray(s0[k]), np.asarray(s1[k])), k
     assert np.allclose(s0[4], s1[4], rtol=1e-5, atol=1e-4) and np.allclose(s0[5], s1[5], rtol=1e-5, atol=1e-4)
+
+
+def test_device_evaluator_equals_the_drop_in_with_gpu_backends(cuda_lib):
+    from casapose_b200.pose_estimation import DeviceEvaluator, estimate_and_evaluate_poses
+    from tests.test_gpu_pipeline import _inputs
+
+    d, cams, offsets, kp3, target_seg, poses_gt, diam = _inputs()
+    b, oc = diam.shape
+    seg = torch.from_numpy(d["seg_logits"]).cuda()
+    tgt = torch.from_numpy(target_seg).cuda()
+    vert = torch.from_numpy(d["vertex"].reshape(b, 240, 320, 18)).cuda()
+    s0, p0, k0 = estimate_and_evaluate_poses(seg, tgt, vert, poses_gt, kp3, cams, diam, offsets, seed=11,
+                                             pnp_backend="cuda", metric_backend="cuda")
+    ev = DeviceEvaluator(kp3[0, :, 0], cams[0], diam[0])
+    s1, p1, k1 = ev(seg, tgt, vert, poses_gt[:, :, 0], offsets, seed=11)
+    assert torch.equal(k0, k1) and torch.equal(p0, p1.cpu())
+    names = ["valid_2d", "valid_3d", "valid_pose_count", "false_positive_mask", "err_2d", "err_3d", "missing_object", "false_positive_pose"]
+    for i, n in enumerate(names):
+        a, c = np.atleast_1d(np.asarray(s0[i], np.float32)), s1[n]
+        assert np.allclose(a, c, rtol=1e-6, atol=1e-5), n

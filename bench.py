@@ -438,6 +438,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = world * B * args.steps / e2e_s
+    # context for e2e: pinned host -> device copy bandwidth of this box, and the bytes the host entry point really
+    # moves (the whole mask by DMA, the vector field only at masked pixels through mapped reads)
+    scratch = torch.empty_like(mask)
+    h2d_gbs = 0.0
+    for _ in range(3):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        scratch.copy_(mask_h, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = max(h2d_gbs, mask_h.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+    del scratch
+    moved_bytes = mask_h.numel() * 4 + float(d["mask"].sum()) * 2 * VN * 4
 
     if rank == 0:
         sum_tn = float(d["mask"].sum())
@@ -457,7 +470,8 @@ def main():
             },
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * OC * VN * 2 * 4,
-                    "ms_per_step": e2e_s / args.steps * 1e3},
+                    "ms_per_step": e2e_s / args.steps * 1e3, "h2d_gbs_measured": h2d_gbs, "bytes_moved_per_step": moved_bytes,
+                    "pcie_floor_ms": moved_bytes / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "fp32", "kernel": "k_score", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",

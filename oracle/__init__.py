@@ -4,13 +4,22 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
 only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it, and only as the checker / the CPU arm.
 
-PARITY UNPINNED.  The reference (/root/reference, fraunhoferhhi/casapose) is pure
+HOW IT IS PINNED.  The reference (/root/reference, fraunhoferhhi/casapose) is pure
 Python on TensorFlow 2.9.1 + tensorflow-addons 0.17.0.  Neither is installed in this
 image (nor on the GPU box) and the reference ships no tests, golden vectors or
-fixtures for this path, so the restatement below cannot be checked against outputs
-of the reference itself.  It is an op-by-op restatement (one float32 rounding per
-TensorFlow op, no fusion) that cites the reference file:line for every function, and
-it is pinned by:
+fixtures for this path.  What pins the restatement instead:
+  * tests/golden/*.npz — outputs of the reference's OWN SOURCE FILES
+    (casapose/pose_estimation/{ransac_voting,voting_layers_2d,pose_evaluation,
+    bpnp_layers}.py, imported unmodified from /root/reference) executed over a numpy
+    stand-in for the TensorFlow API (oracle/tf_standin/, generator oracle/make_golden.py):
+    vote counts of every round, round counts, keypoints, LS-layer outputs, poses and
+    ADD / ADD-S / 2-D verdicts for 14 cases incl. BASELINE configs 1, 2, 3 and 5 at full
+    size.  tests/test_golden_oracle.py: vote counts bit-identical, keypoints <= 1e-3 px,
+    verdicts identical.  This anchors the op order, axis conventions, flips, gates, tie
+    rules and control flow to the reference's code;
+  * what stays UNPINNED is TensorFlow's own kernels (Eigen's float32 summation order and
+    powf, LAPACK-style svd/inv/pinv, tfa's connected components): no TensorFlow can run
+    here, the stand-in uses numpy's / scipy's, and DESIGN.md section 3 lists each choice;
   * a published known-answer vector for the Philox4x32-10 generator (Random123),
   * hand-computed known-answer cases for every degenerate branch,
   * a second, independently written torch-CPU twin that must agree bit-for-bit on

@@ -1,7 +1,8 @@
 """numpy restatement of the reference's weighted least-squares keypoint layer.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py) — PARITY UNPINNED (TensorFlow / tensorflow-addons are
-not installable here; the reference has no tests or golden vectors for this layer).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned by tests/golden/ls_*.npz — the reference's own
+voting_layers_2d.py executed over a numpy TensorFlow stand-in (oracle/make_golden.py); TensorFlow and
+tensorflow-addons themselves are not installable here.
 
 Follows /root/reference/casapose/pose_estimation/voting_layers_2d.py:5-122 op by op in float32,
 with the float64 accumulation the reference itself prescribes (:113-114).  Third-party pieces:

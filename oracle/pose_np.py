@@ -1,6 +1,6 @@
 """Plain-loop restatement of the reference's post-voting PnP and pose metrics.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py) — PARITY UNPINNED.
+TEST INFRASTRUCTURE (see oracle/__init__.py); pinned by tests/golden/ (oracle/make_golden.py).
 Follows /root/reference/casapose/pose_estimation/ransac_voting.py:13-57 (pnp), :92-121
 (transform_points_back_tf), :173-182 (project_tf), :487-558 (map_offsets / map_pnp / estimate_poses),
 :561-687 (map_estimates / evaluate_poses) and pose_evaluation.py:11-101.  OpenCV is a third-party

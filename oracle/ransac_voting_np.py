@@ -1,7 +1,7 @@
 """numpy restatement of the reference's RANSAC keypoint voting.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py) — PARITY UNPINNED (TensorFlow is not
-installable here; the reference has no tests or golden vectors for this path).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned by tests/golden/ (the reference's own source run over a
+numpy TensorFlow stand-in, oracle/make_golden.py); TensorFlow's kernels themselves cannot run here.
 
 Follows /root/reference/casapose/pose_estimation/ransac_voting.py op by op:
 every TensorFlow op is one numpy float32 op, so every intermediate is rounded to

@@ -1,6 +1,6 @@
 """torch-CPU twin of the numpy oracle — the timed "CPU restatement of the reference".
 
-TEST / BENCH INFRASTRUCTURE (see oracle/__init__.py) — PARITY UNPINNED.
+TEST / BENCH INFRASTRUCTURE (see oracle/__init__.py); bit-identical to the numpy oracle, which tests/golden/ pins.
 
 Written independently of oracle/ransac_voting_np.py, one torch op per TensorFlow op of
 /root/reference/casapose/pose_estimation/ransac_voting.py:197-368, and — like the reference —

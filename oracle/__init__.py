@@ -13,7 +13,8 @@ fixtures for this path.  What pins the restatement instead:
     bpnp_layers}.py, imported unmodified from /root/reference) executed over a numpy
     stand-in for the TensorFlow API (oracle/tf_standin/, generator oracle/make_golden.py):
     vote counts of every round, round counts, keypoints, LS-layer outputs, poses and
-    ADD / ADD-S / 2-D verdicts for 14 cases incl. BASELINE configs 1, 2, 3 and 5 at full
+    ADD / ADD-S / 2-D verdicts, and the LS layer's gradient (torch.autograd over the
+    same source on oracle/tf_standin_torch), for 15 cases incl. BASELINE configs 1, 2, 3 and 5 at full
     size.  tests/test_golden_oracle.py: vote counts bit-identical, keypoints <= 1e-3 px,
     verdicts identical.  This anchors the op order, axis conventions, flips, gates, tie
     rules and control flow to the reference's code;

@@ -82,6 +82,18 @@ def ls_filter_inputs():
     return seg, direct, conf
 
 
+def ls_grad_inputs():
+    """One 64x80 frame, 3 objects, plus an incoming gradient g [1,3,9,2].  The background carries small random
+    vectors instead of exact zeros: at an exactly zero vector TensorFlow's autodiff of sqrt gives NaN, the product
+    defines the gradient as 0, and the comparison should not depend on that convention."""
+    seg, direct, conf = ls_inputs(1, 64, 80, (1, 5, 6), seed=77)
+    rng = np.random.default_rng(77)
+    bg = ~direct.any(axis=-1)
+    direct[bg] = (0.05 * rng.normal(size=(int(bg.sum()), 18))).astype(F)
+    g = rng.normal(size=(1, 3, 9, 2)).astype(F)
+    return seg, direct, conf, g
+
+
 def pose_inputs(b, h, w, ids, variant="easy", crop=(0.0, 0.0)):
     """Arguments of estimate_and_evaluate_poses.  crop = (cx, cy): w_crop = dx = cx and h_crop = dy = cy, which
     cancel in transform_points_back_tf (ransac_voting.py:92-121) only if offsets[0,1,4,5] are read in the

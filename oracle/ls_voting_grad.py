@@ -3,8 +3,8 @@
 restated in torch float64 on the CPU and differentiated by torch.autograd — the role TensorFlow's autodiff
 plays in the reference's training step (train_casapose.py:536-595).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py) — the GRADIENT is parity-unpinned (no autodiff of the reference can run
-here; the forward it differentiates is pinned by tests/golden/ls_*.npz).  `hot` (the stop-gradient class weights,
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned by tests/golden/ls_grad.npz: torch.autograd over the reference's
+own voting_layers_2d.py executed on oracle/tf_standin_torch (TensorFlow's autodiff itself cannot run here).  `hot` (the stop-gradient class weights,
 :37-79) comes from oracle.ls_voting_np and is a constant here, as in the reference."""
 import numpy as np
 import torch

@@ -48,6 +48,31 @@ def load_reference():
     return tf, mods
 
 
+def load_reference_ls_torch():
+    """voting_layers_2d.py of the reference, loaded a second time with oracle/tf_standin_torch as ``tensorflow``
+    (torch.autograd then differentiates the graph the reference's own code builds)."""
+    import importlib.util
+
+    standin = os.path.join(ROOT, "oracle", "tf_standin_torch")
+    saved = {k: sys.modules.pop(k, None) for k in ("tensorflow", "tensorflow_addons")}
+    sys.path.insert(0, standin)
+    try:
+        import tensorflow as tft
+
+        assert tft.__version__.endswith("torch-standin")
+        path = os.path.join(REFERENCE, "casapose", "pose_estimation", "voting_layers_2d.py")
+        spec = importlib.util.spec_from_file_location("reference_voting_layers_2d_torch", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(standin)
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+    return mod
+
+
 class PhiloxProvider:
     """Answers tf.random.uniform with oracle/philox_np.py streams; counts rounds per (image, class)."""
 
@@ -189,6 +214,31 @@ def case_ls_filter(tf, mods):
          points_second=_run_ls(mods, seg, direct, conf, filter_estimates=True, output_second_largest_component=True))
 
 
+def case_ls_grad(tf, mods):
+    """Gradient of L = sum(layer(seg, direct, w) * g) w.r.t. direct and w from the reference's own forward code
+    (torch.autograd over oracle/tf_standin_torch), plain softplus weights and filter_estimates + sigmoid weights."""
+    import torch
+
+    from oracle.golden_inputs import ls_grad_inputs
+
+    seg, direct, conf, g = ls_grad_inputs()
+    mod = load_reference_ls_torch()
+    out = {}
+    for tag, kw in (("plain", {}), ("filter_sigmoid", dict(filter_estimates=True, sigmoid_weights=True))):
+        layer = mod.CoordLSVotingWeighted("ls", seg.shape[-1], num_points=9, **kw)
+        td = torch.tensor(direct, requires_grad=True)
+        tw = torch.tensor(conf, requires_grad=True)
+        res = layer([torch.tensor(seg), td, tw])
+        (res * torch.tensor(g)).sum().backward()
+        ref = _run_ls(mods, seg, direct, conf, **kw)  # the numpy stand-in's forward of the same code
+        assert np.abs(res.detach().numpy() - ref).max() < 1e-3
+        out["points_" + tag] = res.detach().numpy().astype(F)
+        out["grad_direct_" + tag] = td.grad.numpy().astype(F)
+        out["grad_conf_" + tag] = tw.grad.numpy().astype(F)
+        assert np.isfinite(out["grad_direct_" + tag]).all() and np.isfinite(out["grad_conf_" + tag]).all()
+    save("ls_grad", input_sha=np.array(sha(seg, direct, conf, g)), **out)
+
+
 def case_ls_full(tf, mods):
     """BASELINE config 1 shape: one 480x640 frame, 8 objects, with and without filter_estimates."""
     from casapose_b200 import synthetic
@@ -261,6 +311,7 @@ CASES = {
     "ls_plain": case_ls_plain,
     "ls_filter": case_ls_filter,
     "ls_full": case_ls_full,
+    "ls_grad": case_ls_grad,
     "pose_eval": case_pose_eval,
     "poses_pnp": case_poses_pnp,
     "unmap": case_unmap,

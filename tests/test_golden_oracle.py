@@ -45,7 +45,7 @@ def golden_counts(g, i, c):
 
 def test_every_golden_file_is_covered():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    assert names == sorted(RANSAC_CASES + ["ls_plain", "ls_filter", "ls_full_480x640", "pose_eval", "poses_pnp",
+    assert names == sorted(RANSAC_CASES + ["ls_plain", "ls_filter", "ls_full_480x640", "ls_grad", "pose_eval", "poses_pnp",
                                            "unmap_offsets", "pose_metric"])
 
 
@@ -122,6 +122,24 @@ def test_ls_full_size_oracle_equals_reference_code():
     assert GI.sha(seg, direct, conf) == str(g["input_sha"])
     assert _check_ls(g["points"], seg, direct, conf).all()
     assert _check_ls(g["points_filter"], seg, direct, conf, filter_estimates=True).all()
+
+
+LS_GRAD_CASES = [("plain", {}), ("filter_sigmoid", {"filter_estimates": True, "sigmoid_weights": True})]
+
+
+@pytest.mark.parametrize("tag,kw", LS_GRAD_CASES)
+def test_ls_gradient_oracle_equals_autodiff_of_reference_code(tag, kw):
+    """tests/golden/ls_grad.npz: torch.autograd over the reference's own voting_layers_2d.py (oracle/tf_standin_torch)."""
+    from oracle import ls_voting_grad as G
+
+    g = load("ls_grad")
+    seg, direct, conf, go = GI.ls_grad_inputs()
+    assert GI.sha(seg, direct, conf, go) == str(g["input_sha"])
+    out, gd, gw = G.ls_vote_with_grads(seg, direct, conf, go, **kw)
+    assert np.abs(out - g["points_" + tag]).max() <= TOL_PX
+    for mine, ref in ((gd, g["grad_direct_" + tag]), (gw, g["grad_conf_" + tag])):
+        assert np.abs(mine - ref).max() <= 2e-5 * np.abs(ref).max()
+        assert np.array_equal(mine != 0, ref != 0)  # gradient exactly on the selected pixels, nowhere else
 
 
 def test_unmap_offsets_oracle_equals_reference_code():

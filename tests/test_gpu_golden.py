@@ -14,7 +14,7 @@ torch = pytest.importorskip("torch")
 from oracle import golden_inputs as GI  # noqa: E402
 from oracle import ls_voting_np as OL  # noqa: E402
 
-from .test_golden_oracle import RANSAC_CASES, _well_conditioned, golden_counts, load, ransac_case_inputs  # noqa: E402
+from .test_golden_oracle import LS_GRAD_CASES, RANSAC_CASES, _well_conditioned, golden_counts, load, ransac_case_inputs  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 TOL_PX = 1e-3
@@ -77,6 +77,23 @@ def test_ls_layer_full_size_equals_reference_code(cuda_lib, key, layer_kw):
     assert GI.sha(seg, direct, conf) == str(g["input_sha"])
     out, ok = _ls(layer_kw, seg, direct, conf)
     assert ok.all() and np.abs(out - g[key]).max() <= TOL_PX
+
+
+@pytest.mark.parametrize("tag,kw", LS_GRAD_CASES)
+def test_ls_backward_equals_autodiff_of_reference_code(cuda_lib, tag, kw):
+    """casa_ls_vote_backward vs torch.autograd over the reference's own layer code (tests/golden/ls_grad.npz)."""
+    from casapose_b200.pose_estimation import CoordLSVotingWeighted
+
+    g = load("ls_grad")
+    seg, direct, conf, go = GI.ls_grad_inputs()
+    assert GI.sha(seg, direct, conf, go) == str(g["input_sha"])
+    layer = CoordLSVotingWeighted("ls", seg.shape[3], **kw)
+    gd, gw = layer.backward([cu(seg), cu(direct), cu(conf)], cu(go))
+    for mine, ref, what in ((gd, g["grad_direct_" + tag], "direct"), (gw, g["grad_conf_" + tag], "conf")):
+        mine = mine.cpu().numpy()
+        assert np.abs(mine - ref).max() <= 2e-4 * np.abs(ref).max(), what
+        differ = (mine != 0) != (ref != 0)
+        assert not differ.any() or max(np.abs(mine[differ]).max(), np.abs(ref[differ]).max()) <= 1e-6 * np.abs(ref).max(), what
 
 
 @pytest.mark.parametrize("pnp_backend,metric_backend", [("cv2", "numpy"), ("cuda", "cuda")])

@@ -181,11 +181,69 @@ __device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const 
 //     |t| < kappa |p| + E        (E = evaluation-error bound of that hypothesis in this chunk)
 // and only units inside it are decided by exact_inlier().  Returns the corrections to the two sign
 // counts.  A NaN hypothesis (no partner / not a filter hypothesis) never enters the band.
+#ifndef CASA_STAGE2_LOOP
+// All kChunk coefficient slots of the chunk are evaluated by one straight-line pass (4 pixels x 2 hypotheses per
+// lane, 8 independent FFMA chains, the shared-memory loads issued together; padding slots hold t = +1e30 and never
+// enter a band), the in-band units — found by 8 % of the passes — are handled afterwards, and the warp reductions
+// run only when some lane has a correction (3 % of the flagged pairs).  The previous form (-DCASA_STAGE2_LOOP)
+// looped over the pixels with a branch per iteration and was latency-bound: 9.5 % of the kernel's instructions but
+// 28 % of its warp-stall samples (profiles/r01_k_score_source_regions.txt).
 __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
                                              float ax, float ay, float bx, float by, float ea, float eb, float kappa2,
                                              const float2* __restrict__ hfilt, int ha, int hb_ok,
                                              const uint32_t* __restrict__ pix, const float2* __restrict__ vd, int t0,
-                                             float thr, unsigned long long* stats) {
+                                             float thr, unsigned& n_exact) {
+  const int lane = threadIdx.x & 31;
+  unsigned inband = 0u;  // bit 2k: hypothesis a at pixel slot k*32+lane, bit 2k+1: hypothesis b
+#pragma unroll
+  for (int k = 0; k < kChunk / 32; ++k) {
+    const float4 A = cA[k * 32 + lane];
+    const float2 B = cB[k * 32 + lane];
+    float pa, pb;
+    const float ta = local_unit(A, B, ax, ay, pa);
+    const float tb = local_unit(A, B, bx, by, pb);
+    inband |= (fabsf(ta) < fmaf(kappa2, fabsf(pa), ea) ? 1u : 0u) << (2 * k);
+    inband |= (fabsf(tb) < fmaf(kappa2, fabsf(pb), eb) ? 1u : 0u) << (2 * k + 1);
+  }
+  if (!hb_ok) inband &= 0x55555555u;
+  int da = 0, db = 0;
+  if (inband) {  // ~1e-5 of the units
+#pragma unroll 1
+    for (int k = 0; k < kChunk / 32; ++k) {
+      const unsigned two = (inband >> (2 * k)) & 3u;
+      const int q = k * 32 + lane;
+      if (two == 0u || q >= npx) continue;
+      const float4 A = cA[q];  // same instructions on the same operands as above: the same t, bit for bit
+      const float2 B = cB[q];
+      float pa, pb;
+      const float ta = local_unit(A, B, ax, ay, pa);
+      const float tb = local_unit(A, B, bx, by, pb);
+      const uint32_t pk = pix[t0 + q];
+      const int x = pk & 0xFFFFu, y = pk >> 16;
+      const float2 dv = load_dir(vd, t0 + q);
+      const float nd = exact_norm(dv.x, dv.y);
+      if (two & 1u) {
+        const float2 h = hfilt[ha];
+        da += (exact_inlier(h.x, h.y, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y, nd, thr) ? 1 : 0) -
+              (int)(__float_as_uint(ta) >> 31);
+      }
+      if (two & 2u) {
+        const float2 h = hfilt[ha + 32];
+        db += (exact_inlier(h.x, h.y, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y, nd, thr) ? 1 : 0) -
+              (int)(__float_as_uint(tb) >> 31);
+      }
+      n_exact += __popc(two);
+    }
+  }
+  if (!__any_sync(0xffffffffu, (da | db) != 0)) return make_int2(0, 0);
+  return make_int2(__reduce_add_sync(0xffffffffu, da), __reduce_add_sync(0xffffffffu, db));
+}
+#else
+__device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
+                                             float ax, float ay, float bx, float by, float ea, float eb, float kappa2,
+                                             const float2* __restrict__ hfilt, int ha, int hb_ok,
+                                             const uint32_t* __restrict__ pix, const float2* __restrict__ vd, int t0,
+                                             float thr, unsigned& n_exact) {
   const int lane = threadIdx.x & 31;
   int da = 0, db = 0;
   for (int q = lane; q < npx; q += 32) {
@@ -211,11 +269,12 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
         db += (exact_inlier(h.x, h.y, (float)x + 0.5f, (float)y + 0.5f, dv.x, dv.y, nd, thr) ? 1 : 0) -
               (int)(__float_as_uint(tb) >> 31);
       }
-      if (stats) atomicAdd(&stats[1], (unsigned long long)(ua ? 1 : 0) + (ub ? 1 : 0));
+      n_exact += (ua ? 1u : 0u) + (ub ? 1u : 0u);
     }
   }
   return make_int2(__reduce_add_sync(0xffffffffu, da), __reduce_add_sync(0xffffffffu, db));
 }
+#endif
 
 // K3 — THE HOT KERNEL.  Persistent grid of independent warps; each warp pulls (job, keypoint,
 // 128-pixel chunk) items from a global counter.  No block barriers.
@@ -242,6 +301,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
   float4* cA = sA[warp];
   float2* cB = sB[warp];
   const float qnan = __int_as_float(0x7fc00000);
+  unsigned n_exact = 0u, n_flagged = 0u;  // per-lane diagnostics, flushed once when the warp leaves
   for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(&a.ws.ctrl[CTRL_WORK], 1);
@@ -375,11 +435,11 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
             const float ax = pa.x - ox, ay = pa.y - oy, bx = pb.x - ox, by = pb.y - oy;  // same h' as the main loop
             const float ea = a.fc.e1 * (oct_norm(ax, ay) + rr), eb = a.fc.e1 * (oct_norm(bx, by) + rr);
             const int2 dd = band_adjust2(cA, cB, npx, ax, ay, bx, by, ea, eb, a.fc.kappa2, hfilt, ha, hb_ok, pix, vd,
-                                         t0, a.fc.thr, a.ws.stats);
+                                         t0, a.fc.thr, n_exact);
             if (lane == 0) {
               if (dd.x) atomicAdd(&gc[ha], dd.x);
               if (dd.y) atomicAdd(&gc[ha + 32], dd.y);
-              atomicAdd(&a.ws.stats[3], 1ull);
+              ++n_flagged;
             }
           }
         }
@@ -393,6 +453,11 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
       const int c = exact_count(pix, vd, t0, npx, hp.x, hp.y, a.fc.thr);
       if (lane == 0 && c) atomicAdd(&gc[h], c);
     }
+  }
+  if (a.ws.stats) {
+    n_exact = __reduce_add_sync(0xffffffffu, n_exact);
+    if (lane == 0 && n_exact) atomicAdd(&a.ws.stats[1], (unsigned long long)n_exact);
+    if (lane == 0 && n_flagged) atomicAdd(&a.ws.stats[3], (unsigned long long)n_flagged);
   }
 }
 

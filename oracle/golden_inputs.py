@@ -114,6 +114,22 @@ def pose_inputs(b, h, w, ids, variant="easy", crop=(0.0, 0.0)):
     return d, cams, offsets, kp3, target_seg, d["poses_gt"][:, :, None].astype(F), diam
 
 
+def pvnet_inputs():
+    """pose_inputs with a PVNet-style vector field [b,h,w,oc*vn*2] — one field per class, wrong (random) everywhere
+    except on the class's own pixels (pose_evaluation.py:38-45 gathers the arg-max class's field and zeroes the
+    background)."""
+    gen = dict(b=1, h=120, w=160, ids=(1, 5, 6, 8))
+    d, cams, offsets, kp3, target_seg, poses_gt, diam = pose_inputs(**gen)
+    oc = len(gen["ids"])
+    rng = np.random.default_rng(21)
+    fields = rng.normal(size=(1, gen["h"], gen["w"], oc, 9, 2)).astype(F)
+    lab = d["seg_logits"].argmax(-1)  # the classes the pre-step will see
+    for c in range(oc):
+        sel = lab[0] == c + 1
+        fields[0, sel, c] = d["vertex"][0, sel]
+    return d, fields.reshape(1, gen["h"], gen["w"], oc * 18), cams, offsets, kp3, target_seg, poses_gt, diam
+
+
 def unmap_inputs(n=12, vn=9, seed=5):
     """Random keypoints and crop / rotate / scale offsets for map_offsets (ransac_voting.py:487-504); rows 0-1
     are all-zero keypoints (the |sum| < 0.01 guard)."""

@@ -29,7 +29,7 @@ F = np.float32
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 from oracle.golden_inputs import (degenerate_scene, ls_filter_inputs, ls_inputs, metric_scene, pose_inputs,  # noqa: E402
-                                  ransac_inputs, sha, unmap_inputs)
+                                  pvnet_inputs, ransac_inputs, sha, unmap_inputs)
 
 
 def load_reference():
@@ -268,6 +268,22 @@ def case_pose_eval(tf, mods):
          **{n: np.asarray(s, F) for n, s in zip(STAT_NAMES, stats)})
 
 
+def case_pose_eval_pvnet(tf, mods):
+    """estimate_and_evaluate_poses with one vector field per class (pose_evaluation.py:38-45) and pose_estimation
+    (:222-269) on the same inputs."""
+    d, fields, cams, offsets, kp3, target_seg, poses_gt, diam = pvnet_inputs()
+    seed = 13
+    tf.random.provider = PhiloxProvider(seed, 9)
+    stats, poses, pts = mods["pose_evaluation"].estimate_and_evaluate_poses(
+        d["seg_logits"], target_seg, fields, poses_gt, kp3, cams, diam, offsets, min_num=20)
+    tf.random.provider = PhiloxProvider(seed, 9)
+    poses2 = mods["pose_evaluation"].pose_estimation(d["seg_logits"], target_seg, fields, poses_gt, kp3, cams, offsets,
+                                                     min_num=20)
+    save("pose_eval_pvnet", input_sha=np.array(sha(d["seg_logits"], fields, target_seg, offsets)), seed=np.int64(seed),
+         poses=np.asarray(poses, F), points=np.asarray(pts, F), poses_pose_estimation=np.asarray(poses2, F),
+         **{n: np.asarray(s, F) for n, s in zip(STAT_NAMES, stats)})
+
+
 def case_poses_pnp(tf, mods):
     """LS layer -> poses_pnp (pose_evaluation.py:164-217): the (y,x)->(x,y) flip, availability from the hard
     softmax, BPNP_fast forward (OpenCV), Rodrigues, t_z flip."""
@@ -313,6 +329,7 @@ CASES = {
     "ls_full": case_ls_full,
     "ls_grad": case_ls_grad,
     "pose_eval": case_pose_eval,
+    "pose_eval_pvnet": case_pose_eval_pvnet,
     "poses_pnp": case_poses_pnp,
     "unmap": case_unmap,
     "pose_metric": case_pose_metric,

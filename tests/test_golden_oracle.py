@@ -45,7 +45,7 @@ def golden_counts(g, i, c):
 
 def test_every_golden_file_is_covered():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    assert names == sorted(RANSAC_CASES + ["ls_plain", "ls_filter", "ls_full_480x640", "ls_grad", "pose_eval", "poses_pnp",
+    assert names == sorted(RANSAC_CASES + ["ls_plain", "ls_filter", "ls_full_480x640", "ls_grad", "pose_eval", "pose_eval_pvnet", "poses_pnp",
                                            "unmap_offsets", "pose_metric"])
 
 
@@ -190,3 +190,21 @@ def test_pose_pipeline_oracle_equals_reference_code():
     assert np.array_equal(res["valid_2d"], g["valid_2d"]) and np.array_equal(res["missing"], g["missing_object"])
     assert np.array_equal(res["valid_count"], g["valid_pose_count"]) and np.array_equal(fp, np.atleast_1d(g["false_positive_mask"]))
     assert np.allclose(res["err_3d"], g["err_3d"], rtol=2e-2, atol=0.5) and np.allclose(res["err_2d"], g["err_2d"], rtol=2e-2, atol=0.05)
+
+
+def test_pvnet_style_fields_oracle_equals_reference_code():
+    """One vector field per class: gather the arg-max class's field, zero on background (pose_evaluation.py:38-45)."""
+    g = load("pose_eval_pvnet")
+    d, fields, cams, offsets, kp3, target_seg, poses_gt, diam = GI.pvnet_inputs()
+    assert GI.sha(d["seg_logits"], fields, target_seg, offsets) == str(g["input_sha"])
+    b, h, w, _ = fields.shape
+    oc = kp3.shape[1]
+    lab = d["seg_logits"].argmax(-1)
+    f6 = fields.reshape(b, h, w, oc, 9, 2)
+    gathered = np.zeros((b, h, w, 9, 2), F)
+    for c in range(oc):
+        gathered[lab == c + 1] = f6[lab == c + 1][:, c]
+    onehot = np.eye(oc + 1, dtype=F)[lab][..., 1:]
+    pts = O.ransac_voting_layer_all_masks(onehot, gathered, 512, min_num=20, seed=int(g["seed"]))
+    assert np.abs(pts - g["points"]).max() <= TOL_PX
+    assert np.array_equal(g["poses"], g["poses_pose_estimation"])  # pose_estimation (:222-269) == the evaluating driver

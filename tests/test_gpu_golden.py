@@ -159,3 +159,38 @@ def test_ls_layer_plus_poses_pnp_equals_reference_code(cuda_lib):
         assert np.array_equal(poses.any(axis=(2, 3, 4)), g["poses"].any(axis=(2, 3, 4))), "availability mask differs"
         assert np.abs(poses[..., :3] - g["poses"][..., :3]).max() < 2e-2, backend
         assert np.abs(poses[..., 3] - g["poses"][..., 3]).max() < 5.0, backend
+
+
+def test_pvnet_style_fields_equal_reference_code(cuda_lib):
+    """vertex [b,h,w,oc*vn*2] through estimate_and_evaluate_poses and pose_estimation (pose_evaluation.py:38-45, 222-269)."""
+    from casapose_b200.pose_estimation import estimate_and_evaluate_poses, pose_estimation
+
+    g = load("pose_eval_pvnet")
+    d, fields, cams, offsets, kp3, target_seg, poses_gt, diam = GI.pvnet_inputs()
+    assert GI.sha(d["seg_logits"], fields, target_seg, offsets) == str(g["input_sha"])
+    stats, poses, pts = estimate_and_evaluate_poses(cu(d["seg_logits"]), cu(target_seg), cu(fields), poses_gt, kp3, cams, diam,
+                                                    offsets, seed=int(g["seed"]))
+    assert np.abs(pts.cpu().numpy() - g["points"]).max() <= TOL_PX
+    valid_2d, valid_3d, valid_count, fp_mask, err_2d, err_3d, missing, fp_pose = [np.asarray(s, F) for s in stats]
+    assert np.array_equal(valid_3d, g["valid_3d"]) and np.array_equal(valid_2d, g["valid_2d"])
+    assert np.array_equal(missing, g["missing_object"]) and np.array_equal(valid_count, g["valid_pose_count"])
+    assert np.allclose(err_3d, g["err_3d"], rtol=2e-2, atol=0.5) and np.allclose(err_2d, g["err_2d"], rtol=2e-2, atol=0.05)
+    p2 = pose_estimation(cu(d["seg_logits"]), cu(target_seg), cu(fields), poses_gt, kp3, cams, offsets, seed=int(g["seed"]))
+    p2 = p2.cpu().numpy() if isinstance(p2, torch.Tensor) else np.asarray(p2)
+    assert np.abs(p2[..., :3] - g["poses_pose_estimation"][..., :3]).max() < 2e-2
+    assert np.abs(p2[..., 3] - g["poses_pose_estimation"][..., 3]).max() < 5.0
+
+
+@pytest.mark.parametrize("name,pinned", [("ransac_full_480x640", True), ("ransac_hard", True), ("ransac_cap", False)])
+def test_host_buffer_entry_equals_reference_code(cuda_lib, name, pinned):
+    """casa_ransac_vote_host (the benchmark's e2e path: zero-copy reads of pinned buffers, staged copy of pageable
+    ones) against the reference code's keypoints."""
+    from casapose_b200.pose_estimation.ransac_voting import ransac_voting_layer_all_masks_host
+
+    g = load(name)
+    mask, vertex, hn, seed, kw = ransac_case_inputs(g)
+    tm, tv = torch.from_numpy(np.ascontiguousarray(mask)), torch.from_numpy(np.ascontiguousarray(vertex))
+    if pinned:
+        tm, tv = tm.pin_memory(), tv.pin_memory()
+    out = ransac_voting_layer_all_masks_host(tm, tv, hn, seed=seed, **kw)
+    assert np.abs(out.numpy() - g["points"]).max() <= TOL_PX

@@ -1,0 +1,89 @@
+"""CPU simulation of the scoring filter's stage-1 flag rate (which hypothesis pairs of a chunk go to stage 2).
+
+Development tool, no GPU: replays k_score's chunk-local bound  min|t| < c1 (max(|h'_a|, |h'_b|) + R)  in float64 on one
+BASELINE config-2 frame with the production Philox hypotheses and reports the flagged fraction of pair x chunk for
+(cur) the shipped pairing (hypotheses h and h+32), (srt) pairs of similar distance to the object, (srt_chunk) pairs of
+similar chunk-local norm, (ideal) a per-hypothesis bound; then how many flagged (hypothesis, chunk) really hold an
+in-band unit and how loose the bound was for the offending pixel.  Round-1 result: cur 2.73 % (ncu: 2.7 %), srt 1.94 %,
+ideal 1.73 % of the pair slots; 49 % of the per-hypothesis flags are real; 79 % of the bounds are within 4x of tight.
+usage: python scripts/sim_flags.py   (imports oracle/ for the hypothesis generation: test infrastructure)"""
+import numpy as np, sys, math
+sys.path.insert(0, __import__('os').path.join(__import__('os').path.dirname(__file__), '..'))
+from casapose_b200 import synthetic
+from oracle import philox_np, ransac_voting_np as O
+u=2.0**-24; thr=0.99
+th0=math.acos(thr); s0=math.sin(th0); dC=1.05*(u+8*u*thr); delta=1.2*(dC/s0+8*u)
+k_lo=math.tan(th0-delta); k_hi=math.tan(th0+delta); kap=1-1/(k_hi/k_lo); e1=12*1.41421357*u; c1=k_hi*kap+e1
+print("c1",c1,"kap",kap,"e1",e1)
+d=synthetic.make_frames(1,480,640,synthetic.CONFIG_8_IDS,variant="easy")
+mask,vertex=d["mask"],d["vertex"]
+def octn(x,y):
+    ax,ay=np.abs(x),np.abs(y); return np.maximum(ax,ay)+0.4142136*np.minimum(ax,ay)
+tot=dict(cur=0,srt=0,ideal=0,n=0, srt_chunk=0)
+for c in range(8):
+    ys,xs=np.nonzero(mask[0,:,:,c])
+    tn=len(ys)
+    if tn<5: continue
+    coords=np.stack([xs,ys],1).astype(np.float32)+0.5
+    direct=vertex[0,ys,xs][:,:,::-1].astype(np.float32)
+    idx=philox_np.draw_idxs(1237,0,c,0,512,9,tn)
+    hyp=O.generate_hypothesis(direct,coords,idx).astype(np.float64)  # [hn,vn,2]
+    ctr=coords.mean(0)
+    for v in range(0,9,2):
+        dv=direct[:,v].astype(np.float64); n=np.hypot(dv[:,0],dv[:,1]); D=dv[:,0]/n; E=dv[:,1]/n
+        h=hyp[:,v]; ok=np.abs(h.sum(1))>1e-6
+        nj=np.hypot(h[:,0]-ctr[0],h[:,1]-ctr[1]); nj[~ok]=np.inf
+        order=np.argsort(nj,kind="stable")
+        nch=(tn+127)//128
+        for ch in range(nch):
+            sl=slice(ch*128,min(tn,ch*128+128))
+            cx,cy=coords[sl,0].astype(np.float64),coords[sl,1].astype(np.float64)
+            ox=0.5*(cx.min()+cx.max()); oy=0.5*(cy.min()+cy.max())
+            rr=octn(cx-ox,cy-oy).max()
+            hx=h[:,0,None]-cx[None]; hy=h[:,1,None]-cy[None]
+            p=D[sl][None]*hy-E[sl][None]*hx
+            s=-k_lo*(D[sl][None]*hx+E[sl][None]*hy)
+            mn=np.abs(np.abs(p)+s).min(1)      # [hn]
+            nh=octn(h[:,0]-ox,h[:,1]-oy)
+            mn[~ok]=np.inf
+            def flags(perm):
+                a=perm.reshape(-1,2,32)   # blocks of 64 slots: pair (l, l+32)
+                ia,ib=a[:,0,:].ravel(),a[:,1,:].ravel()
+                m=np.minimum(mn[ia],mn[ib]); b=c1*(np.maximum(np.where(ok[ia],nh[ia],0),np.where(ok[ib],nh[ib],0))+rr)
+                return (m<b).sum()
+            tot["cur"]+=flags(np.arange(512)); tot["srt"]+=flags(order)
+            # sort by chunk-local norm (upper bound of what any static order can do)
+            tot["srt_chunk"]+=flags(np.argsort(np.where(ok,nh,np.inf),kind="stable"))
+            tot["ideal"]+=((mn<c1*(nh+rr))&ok).sum()/1.0
+            tot["n"]+=256
+print({k:(v/tot["n"] if k!="n" else v) for k,v in tot.items()})
+
+# where do per-hypothesis flags come from?
+import collections
+bins=collections.Counter(); allb=collections.Counter(); true_band=0; flagged_h=0
+for c in range(8):
+    ys,xs=np.nonzero(mask[0,:,:,c]); tn=len(ys)
+    if tn<5: continue
+    coords=np.stack([xs,ys],1).astype(np.float32)+0.5
+    direct=vertex[0,ys,xs][:,:,::-1].astype(np.float32)
+    idx=philox_np.draw_idxs(1237,0,c,0,512,9,tn)
+    hyp=O.generate_hypothesis(direct,coords,idx).astype(np.float64)
+    for v in (0,4):
+        dv=direct[:,v].astype(np.float64); n=np.hypot(dv[:,0],dv[:,1]); D=dv[:,0]/n; E=dv[:,1]/n
+        h=hyp[:,v]; ok=np.abs(h.sum(1))>1e-6
+        for ch in range((tn+127)//128):
+            sl=slice(ch*128,min(tn,ch*128+128))
+            cx,cy=coords[sl,0].astype(np.float64),coords[sl,1].astype(np.float64)
+            ox=0.5*(cx.min()+cx.max()); oy=0.5*(cy.min()+cy.max()); rr=octn(cx-ox,cy-oy).max()
+            hx=h[:,0,None]-cx[None]; hy=h[:,1,None]-cy[None]
+            p=D[sl][None]*hy-E[sl][None]*hx; s=-k_lo*(D[sl][None]*hx+E[sl][None]*hy); t=np.abs(p)+s
+            at=np.abs(t); j=at.argmin(1); mn=at.min(1); nh=octn(h[:,0]-ox,h[:,1]-oy)
+            fl=(mn<c1*(nh+rr))&ok
+            dist=np.hypot(hx,hy)[np.arange(512),j]   # distance of the offending pixel
+            ratio=(nh+rr)/np.maximum(dist,1e-9)
+            for r in ratio[fl]: bins[min(int(np.log2(max(r,1))),8)]+=1
+            # truly uncertain units: |t| < kap*|p| + E
+            Eb=e1*(nh+rr)
+            true_band+=((at<kap*np.abs(p)+Eb[:,None])&ok[:,None]).any(1).sum(); flagged_h+=fl.sum()
+print("flagged hyp-chunks",flagged_h,"of which truly in-band",true_band)
+print("log2((|h'|+R)/dist of offending pixel) histogram:",sorted(bins.items()))

@@ -423,6 +423,8 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
 
   CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
+  // debug copy of the pixel lists takes the whole [b][cap] buffer: define the unused tail (debug calls only)
+  if (dbg.pix) CUDA_TRY(cudaMemsetAsync(ws.pix, 0, (size_t)d.b * d.cap * 4, st));
   h->score_ms = 0.0;
   h->score_launches = 0;
 

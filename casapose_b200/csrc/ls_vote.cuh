@@ -403,8 +403,9 @@ __global__ void __launch_bounds__(256) k_ls_weights(WS ws, Dims d, LsWS lw, LsDi
       w = __fmul_rn(keep ? 1.0f : 0.0f, w);
     }
     wt[t] = w;
-    if (w != 0.f)
-      for (int v = 0; v < d.vn; ++v) cc[(size_t)v * tn + t] = ls_weight(__ldg(conf + p * ld.vn + v), ld.sigmoid_weights);
+    // dropped pixels (weight 0) get defined zeros: k_ls_reduce loads the entry before it looks at the weight
+    for (int v = 0; v < d.vn; ++v)
+      cc[(size_t)v * tn + t] = w != 0.f ? ls_weight(__ldg(conf + p * ld.vn + v), ld.sigmoid_weights) : 0.f;
   }
 }
 
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDim
       lw_[k] = in ? wt[t] : 0.f;
       lp_[k] = in ? pix[t] : 0u;
       ld_[k] = in ? __ldg(vd + t) : make_float2(0.f, 0.f);  // (n0, n1) = (dy, dx)
-      lc_[k] = in ? cc[t] : 0.f;  // (entries with weight 0 hold stale values: never used)
+      lc_[k] = in ? cc[t] : 0.f;  // (entries with weight 0 hold 0 and are skipped below)
     }
 #pragma unroll
     for (int k = 0; k < kRefineTile / 256; ++k) {

@@ -163,6 +163,12 @@ def case_ransac_cap(tf, mods):
     _ransac_case(tf, mods, "ransac_cap", *ransac_inputs(1, 120, 160, (1, 5, 6, 8)), 64, 5, max_num=150)
 
 
+def case_ransac_params(tf, mods):
+    """Non-default parameters: inlier_thresh 0.97, confidence 0.9999 (more rounds), min_num 100 (gates small classes)."""
+    _ransac_case(tf, mods, "ransac_params", *ransac_inputs(2, 96, 128, (1, 5, 6), variant="hard", seed=99), 32, 21,
+                 inlier_thresh=0.97, confidence=0.9999, max_iter=8, min_num=100)
+
+
 def case_ransac_degenerate(tf, mods):
     _ransac_case(tf, mods, "ransac_degenerate", *degenerate_scene(), 32, 3, max_iter=3)
 
@@ -321,6 +327,7 @@ CASES = {
     "ransac_hard": case_ransac_hard,
     "ransac_cap": case_ransac_cap,
     "ransac_degenerate": case_ransac_degenerate,
+    "ransac_params": case_ransac_params,
     "ransac_full": case_ransac_full,
     "ransac_13obj_hard": case_ransac_13obj_hard,
     "ransac_1080p": case_ransac_1080p,

@@ -49,7 +49,7 @@ def test_every_golden_file_is_covered():
                                            "unmap_offsets", "pose_metric"])
 
 
-RANSAC_CASES = ["ransac_easy", "ransac_hard", "ransac_cap", "ransac_degenerate", "ransac_full_480x640",
+RANSAC_CASES = ["ransac_easy", "ransac_hard", "ransac_cap", "ransac_degenerate", "ransac_params", "ransac_full_480x640",
                 "ransac_13obj_hard_480x640", "ransac_1080p_cap"]
 
 
@@ -70,6 +70,8 @@ def test_ransac_oracle_equals_reference_code(name):
     # the same reference code with numpy's float32 summation order in AtA / Atb (:361-362): how much "the order in
     # which TensorFlow adds" is worth — up to 4e-3 px on a 480x640 frame, more at 1080p
     assert np.nanmax(np.abs(pts - g["points_f32_order"])) <= 3e-2
+    if name == "ransac_params":
+        assert g["rounds"].tolist() == [[0, 6, 0], [7, 7, 5]]  # min_num gate, data-dependent exits below max_iter = 8
     if name == "ransac_hard" or name.startswith("ransac_13obj"):
         assert int(g["rounds"].max()) > 1
     if name == "ransac_degenerate":

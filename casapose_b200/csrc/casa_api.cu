@@ -432,6 +432,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   sa.ws = ws;
   sa.d = d;
   sa.fc = fc;
+  sa.one = 1u;
   if (h->score_occ == 0) {
     if (h->score_p == 4)
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<4>, kScoreThreads, 0));

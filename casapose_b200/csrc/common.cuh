@@ -35,12 +35,10 @@ constexpr int CTRL_WORDS = 8;
 // Constants of the filtered predicate, derived on the host in double (filter_consts()).
 struct FilterConsts {
   float thr;     // inlier_thresh as float32
-  float k_lo;    // tan(theta0 - delta), rounded down
-  float rho;     // k_hi / k_lo, rounded up (> 1)
-  float kappa;   // 1 - 1/rho, rounded up:  |p| < rho a  <=>  |p| - a - kappa |p| < 0
+  float k_mid;   // tan(theta0): t = |p| + s changes sign exactly at the threshold angle
   float c1;      // k_score: a chunk's signs are proven if min|t| >= c1 (|h'| + R)
-  float e1;      // k_score stage 2: evaluation-error bound of t is e1 (|h'| + R)
-  float kappa2;  // k_score stage 2: kappa with the slack for the error of |p|
+  float e1;      // k_score stage 2: evaluation-error part of the unit band, e1 (|h'| + R)
+  float kappa2;  // k_score stage 2: a unit is uncertain only if |t| < kappa2 |p| + e1 (|h'| + R)
   int fast_ok;   // 0 -> thresholds outside the proven range, score everything exactly
 };
 

@@ -67,6 +67,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
+// Sum of the four sign counters.  PRMT form: every negative unit added 0xFFFF to one of the two 16-bit fields of a
+// counter, i.e. the counter is -(n_lo) in the low field and -(n_hi) - borrow in the high field.
+__device__ __forceinline__ unsigned decode4(const unsigned (&c)[4]) {
+  unsigned n = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#ifdef CNT_PRMT
+    const unsigned lo = (0u - c[k]) & 0xFFFFu;
+    const unsigned hi = (0u - ((c[k] + lo) >> 16)) & 0xFFFFu;  // c + lo has a zero low field (carry into the high one)
+    n += lo + hi;
+#else
+    n += c[k];
+#endif
+  }
+  return n;
+}
+
 __global__ void __launch_bounds__((kEpiWarps + 1) * 32, 1)
 k_tc_epilogue(const float* __restrict__ A, const float* __restrict__ B, int iters, unsigned* __restrict__ counts,
               float* __restrict__ mins) {
@@ -116,6 +133,7 @@ k_tc_epilogue(const float* __restrict__ A, const float* __restrict__ B, int iter
     // ---------------------------------------------------------------- epilogue: thread = one hypothesis, 64 pixels
     const int quarter = warp & 3, half = warp >> 2;
     unsigned cnt4[4] = {0u, 0u, 0u, 0u};  // four independent chains: one thread has no other ILP here
+    unsigned total = 0u;
     float mn4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
     for (int it = 0; it < iters; ++it) {
       const int s = it & 1;
@@ -128,6 +146,22 @@ k_tc_epilogue(const float* __restrict__ A, const float* __restrict__ B, int iter
         tmem_ld32(lane_base + (uint32_t)(half * 64 + j0), p);          // p of 32 pixels
         tmem_ld32(lane_base + (uint32_t)(kPix + half * 64 + j0), q);   // s of the same pixels
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef CNT_PRMT
+        // sign count with PRMT (sign-replicating byte permute: 0xFFFF per negative t, two units) + IADD3 over two
+        // pairs: 3 ALU-pipe instructions per 4 units instead of 4 LEA.HI; the two 16-bit fields are decoded at the end
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) t[u] = fabsf(__uint_as_float(p[j + u])) + __uint_as_float(q[j + u]);
+          unsigned r0, r1;
+          asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(r0) : "r"(__float_as_uint(t[0])), "r"(__float_as_uint(t[1])));
+          asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(r1) : "r"(__float_as_uint(t[2])), "r"(__float_as_uint(t[3])));
+          cnt4[(j >> 2) & 3] = cnt4[(j >> 2) & 3] + r0 + r1;
+          mn4[(j >> 2) & 3] = fminf(fminf(mn4[(j >> 2) & 3], fabsf(t[0])), fabsf(t[1]));
+          mn4[((j >> 2) + 2) & 3] = fminf(fminf(mn4[((j >> 2) + 2) & 3], fabsf(t[2])), fabsf(t[3]));
+        }
+#else
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const float t0 = fabsf(__uint_as_float(p[j])) + __uint_as_float(q[j]);
@@ -136,12 +170,17 @@ k_tc_epilogue(const float* __restrict__ A, const float* __restrict__ B, int iter
           cnt4[((j >> 1) + 2) & 3] += __float_as_uint(t1) >> 31;
           mn4[(j >> 1) & 3] = fminf(fminf(mn4[(j >> 1) & 3], fabsf(t0)), fabsf(t1));
         }
+#endif
       }
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+      if ((it & 255) == 255) {  // the 16-bit fields of the PRMT form hold 256 tiles of 64 pixels
+        total += decode4(cnt4);
+        cnt4[0] = cnt4[1] = cnt4[2] = cnt4[3] = 0u;
+      }
     }
-    const unsigned cnt = cnt4[0] + cnt4[1] + cnt4[2] + cnt4[3];
+    const unsigned cnt = total + decode4(cnt4);
     const float mn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
     const int hyp = quarter * 32 + lane;
     counts[((size_t)blockIdx.x * kM + hyp) * 2 + half] = cnt;

@@ -31,11 +31,11 @@ constexpr uint32_t kTmemCols = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(kLBO >> 4) << 16;
-  d |= (uint64_t)(kSBO >> 4) << 32;
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version of sm_100
   return d;                // base offset 0, LBO mode 0, SWIZZLE_NONE
 }
@@ -48,7 +48,7 @@ __device__ __forceinline__ uint32_t tile_offset(int row, int k) {  // byte offse
   return (uint32_t)((row & 7) * 16 + (row >> 3) * kSBO + (k & 3) * 4 + (k >> 2) * kLBO);
 }
 
-__global__ void __launch_bounds__(128, 1) k_tc_probe(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+__global__ void __launch_bounds__(128, 1) k_tc_probe(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, uint32_t lbo, uint32_t sbo) {
   __shared__ __align__(128) uint8_t sA[kM / 8 * kSBO];  // 4 KB
   __shared__ __align__(128) uint8_t sB[kN / 8 * kSBO];  // 8 KB
   __shared__ __align__(8) uint64_t bar;
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(128, 1) k_tc_probe(const float* __restrict__ A
   const uint32_t tmem_base = tmem_base_smem;
 
   if (tid == 0) {  // a single thread issues the MMA on behalf of the CTA
-    const uint64_t adesc = make_smem_desc(smem_u32(sA));
-    const uint64_t bdesc = make_smem_desc(smem_u32(sB));
+    const uint64_t adesc = make_smem_desc(smem_u32(sA), lbo, sbo);
+    const uint64_t bdesc = make_smem_desc(smem_u32(sB), lbo, sbo);
     const uint32_t idesc = make_idesc();
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -140,7 +140,8 @@ static float tf32_round(float x) {  // round to nearest, ties away (cvt.rna.tf32
     }                                                                              \
   } while (0)
 
-int main() {
+int main(int argc, char** argv) {
+  const bool swap = argc > 1 && !strcmp(argv[1], "swap");  // descriptor fields exchanged (layout in memory unchanged)
   static float hA[kM * kK], hB[kN * kK], hD[kM * kN];
   srand(1);
   // A rows: [hx_hi, hx_lo, hx_hi, hy_hi, hy_lo, hy_hi, 1, 1]; B rows: p | s coefficient splits (random stand-ins)
@@ -164,7 +165,7 @@ int main() {
   CK(cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xff, sizeof(hD)));
-  k_tc_probe<<<1, 128>>>(dA, dB, dD);
+  k_tc_probe<<<1, 128>>>(dA, dB, dD, swap ? kSBO : kLBO, swap ? kLBO : kSBO);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(hD, dD, sizeof(hD), cudaMemcpyDeviceToHost));
@@ -181,7 +182,7 @@ int main() {
       if (!(err < 1e-5)) ++bad;
       if (err > worst || err != err) worst = err;
     }
-  printf("tc_probe: max |D - ref| / sum|terms| = %.3g (%.2f u), %d of %d entries off\n", worst, worst / 5.96e-8, bad, kM * kN);
+  printf("tc_probe%s: max |D - ref| / sum|terms| = %.3g (%.2f u), %d of %d entries off\n", swap ? " (LBO/SBO fields swapped)" : "", worst, worst / 5.96e-8, bad, kM * kN);
   if (bad == 0) printf("tc_probe ok\n");
   return bad != 0;
 }

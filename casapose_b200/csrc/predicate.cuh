@@ -4,19 +4,19 @@
 //  * exact_inlier(): the reference's float32 op sequence, one IEEE rounding per TensorFlow
 //    op (__f*_rn intrinsics are never contracted into FMAs).  This DEFINES the result.
 //
-//  * the filtered predicate: per (pixel, keypoint) the unit direction d^ = d/|d| is turned
-//    into two linear forms of hd = fl(h - c) (the same rounded difference the reference
-//    uses, :236):
-//        p  = d^ x hd            (= |hd| sin(theta))
-//        a  = k_lo * (d^ . hd)   (= k_lo |hd| cos(theta)),     a_hi = rho * a
-//    "|p| < a"    proves  theta < theta0 - delta  => the reference says inlier,
-//    "|p| >= a_hi" proves theta > theta0 + delta  => the reference says outlier,
-//    where theta0 = acos(inlier_thresh) and delta covers (i) the worst-case rounding of
-//    the reference's own sequence around the true cosine and (ii) the rounding of the
-//    filter (derivation in DESIGN.md section "Filtered predicate").  Units in between
-//    (~1e-5 of all units) are re-evaluated with exact_inlier().  Vote counts are
-//    therefore bit-identical to the exact sequence while the common path costs
-//    7 FP32-pipe + 2 compare instructions per unit instead of ~30.
+//  * the filtered predicate (chunk-local form, what k_score evaluates): per (pixel, keypoint) the unit
+//    direction d^ = d/|d| is turned into two linear forms of hd = h - c,
+//        p = d^ x hd            (= |hd| sin(theta))
+//        s = -k (d^ . hd)       (= -k |hd| cos(theta)),      k = tan(theta0),  theta0 = acos(inlier_thresh)
+//    so that  t = |p| + s = |hd| sin(theta - theta0) / cos(theta0)  is negative exactly for theta < theta0.
+//    The band is CENTRED on the threshold: sign(t) is the reference's verdict whenever
+//        |t| >= w |hd| + E,        w = sin(delta) / cos(theta0)
+//    where delta covers (i) the worst-case rounding of the reference's own sequence around the true
+//    cosine and (ii) the rounding of the filter's coefficients, and E is the evaluation error of t
+//    (derivation: filter_consts() below and DESIGN.md "Filtered predicate"; executable check:
+//    scripts/check_band.py).  Units inside the band (~2e-5 of all units) are re-evaluated with
+//    exact_inlier().  Vote counts are therefore bit-identical to the exact sequence while the common path
+//    costs 5 FP32-pipe instructions per unit instead of ~30.
 #pragma once
 #include <math.h>
 
@@ -63,9 +63,8 @@ __device__ __forceinline__ float2 exact_hypothesis(float2 c0, float2 c1, float2 
 // ---------------------------------------------------------------- filtered predicate
 
 struct PixCoef {
-  float cx, cy;  // pixel centre (x+.5, y+.5)
-  float D, E;    // d^ = (dx, dy) / |d|
-  float G, H;    // k_lo * d^
+  float D, E;  // d^ = (dx, dy) / |d|
+  float G, H;  // k * d^
 };
 
 // float32 bit pattern of the smallest q with sqrt_rn(q) > 1e-6f (sqrt_rn is monotone), so that
@@ -74,9 +73,7 @@ struct PixCoef {
 constexpr uint32_t kNormSqMinBits = 0x2b8cbcceu;  // 1.0000002e-12f
 
 // Returns false if this (pixel, keypoint) cannot use the filter (non-finite or huge direction).
-__device__ __forceinline__ bool make_coef(float cx, float cy, float dx, float dy, float k_lo, PixCoef& c) {
-  c.cx = cx;
-  c.cy = cy;
+__device__ __forceinline__ bool make_coef(float dx, float dy, float k, PixCoef& c) {
   c.D = c.E = c.G = c.H = 0.f;  // zero forms: never an inlier
   const float ax = fabsf(dx), ay = fabsf(dy);
   if (!(ax <= kDirMax && ay <= kDirMax)) return false;  // also catches NaN / inf
@@ -85,28 +82,10 @@ __device__ __forceinline__ bool make_coef(float cx, float cy, float dx, float dy
     const float inv = rsqrtf(q);               // 2 ulp; a common scale of (D,E,G,H) cannot change a sign
     c.D = dx * inv;
     c.E = dy * inv;
-    c.G = k_lo * c.D;
-    c.H = k_lo * c.E;
+    c.G = k * c.D;
+    c.H = k * c.E;
   }
   return true;
-}
-
-// One unit of the filter.  inlier-for-sure <=> sign(tlo), maybe-inlier <=> sign(thi).
-// Negated form on purpose: NaN (canonical, sign 0) and +0 are "not inlier", and neither chain can yield -0.
-__device__ __forceinline__ void filter_unit(float cx, float cy, float D, float nE, float nG, float nH, float nkappa,
-                                            float hx, float hy, float& tlo, float& thi) {
-  const float hdx = hx - cx;  // same rounded difference as the reference (:236)
-  const float hdy = hy - cy;
-  const float pv = fmaf(D, hdy, __fmul_rn(nE, hdx));
-  tlo = fmaf(nG, hdx, fmaf(nH, hdy, fabsf(pv)));
-  thi = fmaf(nkappa, fabsf(pv), tlo);
-}
-
-__device__ __forceinline__ void filter_test(const PixCoef& c, float hx, float hy, float kappa, bool& lo, bool& hi) {
-  float tlo, thi;
-  filter_unit(c.cx, c.cy, c.D, -c.E, -c.G, -c.H, -kappa, hx, hy, tlo, thi);
-  lo = (__float_as_uint(tlo) >> 31) != 0u;
-  hi = (__float_as_uint(thi) >> 31) != 0u;
 }
 
 // ---------------------------------------------------------------- chunk-local form (what k_score evaluates)
@@ -119,11 +98,11 @@ __device__ __forceinline__ float oct_norm(float x, float y) {
 // Coefficients of one pixel relative to the chunk origin o: (cxl, cyl) = c - o (exact).
 //   A = (D, -E, -P0, A0), B = (-G, -H);  invalid pixels (|d| <= 1e-6): t = +1e30 for every hypothesis.
 // Returns false if the direction cannot use the filter (non-finite / huge).
-__device__ __forceinline__ bool make_local_coef(float cxl, float cyl, float dx, float dy, float k_lo, float4& A, float2& B) {
+__device__ __forceinline__ bool make_local_coef(float cxl, float cyl, float dx, float dy, float k, float4& A, float2& B) {
   A = make_float4(0.f, 0.f, 0.f, 1.0e30f);
   B = make_float2(0.f, 0.f);
   PixCoef pc;
-  if (!make_coef(0.f, 0.f, dx, dy, k_lo, pc)) return false;
+  if (!make_coef(dx, dy, k, pc)) return false;
   if (pc.D != 0.f || pc.E != 0.f) {
     A = make_float4(pc.D, -pc.E, -(pc.D * cyl - pc.E * cxl), pc.G * cxl + pc.H * cyl);
     B = make_float2(-pc.G, -pc.H);
@@ -152,12 +131,29 @@ __device__ __forceinline__ int classify_hypothesis(float hx, float hy, bool fast
 
 // ---------------------------------------------------------------- host: filter constants
 
+// Derivation (u = 2^-24; theta = angle between the stored direction d and the reference's hd = fl(h - c)):
+//  (1) the reference's float32 sequence (:236-247) returns ang with |ang - cos(theta)| <= u + 7u|cos(theta)| + O(u^2):
+//      the two products and the sum of `dot` give |d||hd| u (1 + |cos| + u), each norm carries 2u (two squares and
+//      a sum of positive terms, halved by the root, plus the root's own rounding), their product u, the divide u.
+//      dC = 1.05 (u + 8u thr) bounds that for every theta near the threshold; in angle d_ref = dC / sin(theta0).
+//  (2) the filter's own direction (D,E) = fl(d * rsqrt(q)) and (G,H) = fl(k (D,E)) deviate from d^ by < 3u of angle
+//      (component roundings; the common scale error of rsqrt cannot change a sign), k = fl(tan(theta0)) by < 1u:
+//      d_fil = 8u.
+//  (3) delta = 1.2 (d_ref + d_fil); cos(theta0 -+ delta) is checked against thr +- dC below, so every unit with
+//      |theta - theta0| >= delta is decided by the reference exactly as sign(theta - theta0) says.
+//  (4) real arithmetic: t* = |hd| sin(theta - theta0)/cos(theta0), so |theta - theta0| < delta  =>  |t*| < w |hd|,
+//      w = sin(delta)/cos(theta0).  The evaluated t differs from t* by at most e (|h'| + R): 6u (|h'|_1 + |c'|_1)
+//      from the two FMA chains, the final add and the coefficient roundings, 2 sqrt2 (1+k) u (|h'| + R) from
+//      h' - c' = fl(h - o) - (c - o) standing in for fl(h - c);  e1 = 12 sqrt2 u covers both with a factor 1.45.
+//  (5) chunk level: |hd| <= |h'| + R, hence  min|t| >= c1 (|h'| + R),  c1 = w + e1,  proves every sign of the chunk;
+//      unit level (stage 2): inside the band |p*| >= |hd| sin(theta0 - delta), hence a unit can be uncertain only if
+//      |t| < kappa2 |p| + e2 (|h'| + R),  kappa2 = w / sin(theta0 - delta),  e2 = (1 + kappa2) e1.
+// scripts/check_band.py evaluates (1), (4) and (5) against float64 on adversarial grids; casa_selftest_filter
+// does the same on the device against exact_inlier().
 inline FilterConsts filter_consts(float inlier_thresh, int force_exact) {
   FilterConsts f;
   f.thr = inlier_thresh;
-  f.k_lo = 0.f;
-  f.rho = 1.f;
-  f.kappa = 0.f;
+  f.k_mid = 0.f;
   f.c1 = 0.f;
   f.e1 = 0.f;
   f.kappa2 = 0.f;
@@ -167,35 +163,20 @@ inline FilterConsts filter_consts(float inlier_thresh, int force_exact) {
   const double u = 5.9604644775390625e-8;  // 2^-24
   const double theta0 = acos(thr);
   const double s0 = sin(theta0);
-  // |ang_reference - cos(theta)| <= (u + 8 u thr) (1 + small): dot (u/thr + u), two norms (2u each),
-  // their product (u), the divide (u), relative to cos(theta) ~ thr.
   const double dC = 1.05 * (u + 8.0 * u * thr);
   const double d_ref = dC / s0;   // angular half-width from the reference's own rounding
-  const double d_fil = 8.0 * u;   // angular error of the filter's two linear forms (< 3.5 u)
-  const double delta = 1.2 * (d_ref + d_fil);  // both terms are worst-case first-order bounds; 20 % covers second order
+  const double d_fil = 8.0 * u;   // angular error of the filter's two linear forms
+  const double delta = 1.2 * (d_ref + d_fil);
   if (!(theta0 - delta > 1e-3)) return f;
   // verify the band really covers dC on both sides (curvature of cos)
   if (!(cos(theta0 - delta) >= thr + dC && cos(theta0 + delta) <= thr - dC)) return f;
-  const double k_lo = tan(theta0 - delta);
-  const double k_hi = tan(theta0 + delta);
-  float klo_f = (float)k_lo;
-  klo_f = nextafterf(klo_f, 0.f);  // rounded down
-  klo_f = nextafterf(klo_f, 0.f);
-  float rho_f = (float)(k_hi / (double)klo_f);
-  for (int i = 0; i < 3; ++i) rho_f = nextafterf(rho_f, 2.f);  // rounded up, + the rounding of rho*a
-  f.k_lo = klo_f;
-  f.rho = rho_f;
-  float kap = (float)(1.0 - 1.0 / (double)rho_f);
-  for (int i = 0; i < 2; ++i) kap = nextafterf(kap, 1.f);
-  f.kappa = kap;
-  // k_score (chunk-local coordinates, derivation in DESIGN.md "Filtered predicate"):
-  //   * the evaluation error of t is below 6 u (|h'|_1 + |c'|_1) <= 6 sqrt2 u (|h'| + R); doubled -> e1;
-  //   * a unit is uncertain only if -E < T < kappa |p| + E, and then |p| < k_hi |hd| <= k_hi (|h'| + R),
-  //     so min|t| >= (k_hi kappa + e1)(|h'| + R) proves every sign of the chunk.
+  f.k_mid = (float)tan(theta0);
+  const double w = sin(delta) / cos(theta0);
+  const double kappa2 = w / sin(theta0 - delta);
   const double e1 = 12.0 * 1.41421357 * u;
-  f.e1 = (float)(1.001 * e1);
-  f.kappa2 = (float)(1.001 * (double)kap);
-  f.c1 = (float)(1.001 * (k_hi * 1.001 * (double)kap + 1.001 * e1));
+  f.e1 = (float)(1.001 * (1.0 + kappa2) * e1);
+  f.kappa2 = (float)(1.001 * kappa2);
+  f.c1 = (float)(1.001 * (w + e1));
   f.fast_ok = 1;
   return f;
 }

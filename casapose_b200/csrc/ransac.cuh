@@ -158,7 +158,15 @@ struct ScoreArgs {
   WS ws;
   Dims d;
   FilterConsts fc;
+  unsigned one;  // 1, opaque to the compiler: keeps the sign accumulation an IMAD (FMA pipe) instead of an ALU-pipe add
 };
+
+// 0xFFFF in the low / high half of the result if a / b has its sign bit set (PRMT with sign-replicating selectors).
+__device__ __forceinline__ unsigned prmt_sign2(float a, float b) {
+  unsigned r;
+  asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(r) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)));
+  return r;
+}
 
 constexpr int kHypPerLane = 8;
 
@@ -285,7 +293,10 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
 //        p = D hy' - E hx' - P0          (= d^ x (h - c))
 //        s = A0 - G hx' - H hy'          (= -k_lo d^ . (h - c))
 //        t = |p| + s                     inlier <=> sign(t)
-//    5 FP32-pipe instructions + 1 LEA.HI (sign count) + 1/2 FMNMX3 per unit;
+//    5 FP32-pipe instructions per unit; the sign bits of a hypothesis pair are turned into two 16-bit fields by one
+//    PRMT and accumulated by one IMAD (FMA pipe) — every negative unit adds 0xFFFF to its field, decoded after the
+//    chunk — i.e. 1/2 PRMT + 1/2 IMAD + 1/2 FMNMX3 per unit (the LEA.HI per unit of the first version cost two
+//    dispatch cycles: profiles/r02_loop_bench.txt);
 //  * every lane owns 8 hypotheses and their private counters (no shuffles/ballots/atomics in the loop);
 //  * min |t| per hypothesis pair is compared with B = c1 (|h'| + R): if min|t| >= B every sign in the
 //    chunk is provably the reference's verdict (predicate.cuh / DESIGN.md); otherwise band_adjust()
@@ -358,7 +369,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
       if (px[k] >= 0) {
         const float cxl = ((float)px[k] + 0.5f) - ox, cyl = ((float)py[k] + 0.5f) - oy;  // c' = c - o, exact
         rr = fmaxf(rr, oct_norm(cxl, cyl));
-        weird |= !make_local_coef(cxl, cyl, dvs[k].x, dvs[k].y, a.fc.k_lo, A, B);
+        weird |= !make_local_coef(cxl, cyl, dvs[k].x, dvs[k].y, a.fc.k_mid, A, B);
       }
       cA[q] = A;
       cB[q] = B;
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     const float2* hfilt = a.ws.hyp_filt + hoff;
     for (int g = 0; g < n_groups; ++g) {
       float hx[kHypPerLane], hy[kHypPerLane], mn[kHypPerLane / 2];
-      unsigned nlo[kHypPerLane];
+      unsigned acc[kHypPerLane / 2];  // two 16-bit sign counters per hypothesis pair (a 128-pixel chunk cannot overflow them)
 #pragma unroll
       for (int i = 0; i < kHypPerLane; ++i) {
         const int h = (g * kHypPerLane + i) * 32 + lane;
@@ -391,10 +402,12 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
         if (h < hn) hp = hfilt[h];
         hx[i] = hp.x - ox;  // h' = fl(h - o)
         hy[i] = hp.y - oy;
-        nlo[i] = 0u;
       }
 #pragma unroll
-      for (int i = 0; i < kHypPerLane / 2; ++i) mn[i] = 3.0e38f;
+      for (int i = 0; i < kHypPerLane / 2; ++i) {
+        mn[i] = 3.0e38f;
+        acc[i] = 0u;
+      }
 #pragma unroll 2
       for (int q = 0; q < npx; ++q) {
         const float4 A = cA[q];
@@ -404,10 +417,15 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
           float p0, p1;
           const float t0v = local_unit(A, B, hx[i], hy[i], p0);
           const float t1v = local_unit(A, B, hx[i + 1], hy[i + 1], p1);
-          nlo[i] += __float_as_uint(t0v) >> 31;
-          nlo[i + 1] += __float_as_uint(t1v) >> 31;
+          acc[i >> 1] = prmt_sign2(t0v, t1v) * a.one + acc[i >> 1];
           mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t0v)), fabsf(t1v));
         }
+      }
+      unsigned nlo[kHypPerLane];
+#pragma unroll
+      for (int i = 0; i < kHypPerLane; i += 2) {  // acc = 0xFFFF n_lo + 0xFFFF0000 n_hi  (mod 2^32)
+        nlo[i] = (0u - acc[i >> 1]) & 0xFFFFu;
+        nlo[i + 1] = (nlo[i] - ((acc[i >> 1] + nlo[i]) >> 16)) & 0xFFFFu;
       }
       // pairs whose closest unit is inside the uncertainty bound (NaN compares false)
       unsigned flagged = 0u;

@@ -33,14 +33,8 @@ __global__ void __launch_bounds__(256) k_selftest_filter(unsigned long long n, u
     const float hx = (float)((double)cx + dist * cos(phir + sgn * th));
     const float hy = (float)((double)cy + dist * sin(phir + sgn * th));
     if (classify_hypothesis(hx, hy, true) != 0) continue;
-    PixCoef pc;
-    if (!make_coef(cx, cy, dx, dy, fc.k_lo, pc)) continue;
-    bool lo, hi;
-    filter_test(pc, hx, hy, fc.kappa, lo, hi);
     const bool ex = exact_inlier(hx, hy, cx, cy, dx, dy, exact_norm(dx, dy), fc.thr);
     ++tested;
-    bad += (lo && !ex) || (!hi && ex) || (lo && !hi);
-    unc += (hi && !lo);
     inl += ex;
     // ---- the chunk-local form exactly as k_score evaluates it: random chunk origin within 90 px of the pixel
     // (one fractional bit, like a bounding-box centre), chunk radius >= this pixel's offset
@@ -48,7 +42,7 @@ __global__ void __launch_bounds__(256) k_selftest_filter(unsigned long long n, u
     const float cxl = cx - ox, cyl = cy - oy;
     float4 A;
     float2 B;
-    if (!make_local_coef(cxl, cyl, dx, dy, fc.k_lo, A, B)) continue;
+    if (!make_local_coef(cxl, cyl, dx, dy, fc.k_mid, A, B)) continue;
     const float hxl = hx - ox, hyl = hy - oy;
     float pl;
     const float t = local_unit(A, B, hxl, hyl, pl);

@@ -6,6 +6,7 @@ BASELINE config-2 frame with the production Philox hypotheses and reports the fl
 similar chunk-local norm, (ideal) a per-hypothesis bound; then how many flagged (hypothesis, chunk) really hold an
 in-band unit and how loose the bound was for the offending pixel.  Round-1 result: cur 2.73 % (ncu: 2.7 %), srt 1.94 %,
 ideal 1.73 % of the pair slots; 49 % of the per-hypothesis flags are real; 79 % of the bounds are within 4x of tight.
+Round 2 (band centred on the threshold, c1 = w + e1 instead of k_hi kappa + e1): see the printed numbers.
 usage: python scripts/sim_flags.py   (imports oracle/ for the hypothesis generation: test infrastructure)"""
 import numpy as np, sys, math
 sys.path.insert(0, __import__('os').path.join(__import__('os').path.dirname(__file__), '..'))
@@ -13,7 +14,7 @@ from casapose_b200 import synthetic
 from oracle import philox_np, ransac_voting_np as O
 u=2.0**-24; thr=0.99
 th0=math.acos(thr); s0=math.sin(th0); dC=1.05*(u+8*u*thr); delta=1.2*(dC/s0+8*u)
-k_lo=math.tan(th0-delta); k_hi=math.tan(th0+delta); kap=1-1/(k_hi/k_lo); e1=12*1.41421357*u; c1=k_hi*kap+e1
+k_lo=math.tan(th0); w=math.sin(delta)/math.cos(th0); kap=w/math.sin(th0-delta); e1=12*1.41421357*u; c1=w+e1  # centred band (round 2); k_lo is k_mid now
 print("c1",c1,"kap",kap,"e1",e1)
 d=synthetic.make_frames(1,480,640,synthetic.CONFIG_8_IDS,variant="easy")
 mask,vertex=d["mask"],d["vertex"]

@@ -58,7 +58,6 @@ struct casa_handle {
   int score_occ = 0;
   int use_graph = 1;
   std::vector<struct casa_graph*> graphs;
-  int score_p = 3;  // min resident blocks/SM the scoring kernel is compiled for (3: 80 regs, 4: 64 regs)
 };
 
 struct casa_graph {
@@ -93,8 +92,6 @@ extern "C" int casa_create(int device, casa_handle** out) {
   CUDA_TRY(cudaEventCreate(&h->ev1));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_round, cudaEventDisableTiming));
   if (getenv("CASA_NO_GRAPH")) h->use_graph = 0;
-  const char* sp = getenv("CASA_SCORE_MINB");
-  if (sp && atoi(sp) == 4) h->score_p = 4;
   *out = h;
   return CASA_OK;
 }
@@ -141,7 +138,7 @@ size_t bump(size_t& cur, size_t bytes) {
 }
 
 
-int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
+int make_layout(const casa_ransac_params* p, Layout& L) {
   if (!p) return fail(CASA_ERR_INVALID, "params is NULL");
   if (p->b < 1 || p->h < 1 || p->w < 1 || p->h > 65535 || p->w > 65535)
     return fail(CASA_ERR_INVALID, "bad shape b=%d h=%d w=%d", p->b, p->h, p->w);
@@ -163,7 +160,6 @@ int make_layout(const casa_ransac_params* p, int score_p, Layout& L) {
   if (rtiles > (1ll << 30) || (long long)d.b * ((long long)d.cap / kChunk + d.oc + 1) * d.vn > (1ll << 30))
     return fail(CASA_ERR_INVALID, "too many work items");
   d.max_rtiles = (int)rtiles;
-  (void)score_p;
   d.image_offset = p->image_offset;
   d.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFull);
   d.seed_hi = (uint32_t)(p->seed >> 32);
@@ -247,7 +243,7 @@ int ensure(void** mem, size_t* have, size_t need) {
 
 extern "C" size_t casa_ransac_workspace_bytes(const casa_ransac_params* p) {
   Layout L;
-  if (make_layout(p, 4, L) != CASA_OK) return 0;
+  if (make_layout(p, L) != CASA_OK) return 0;
   return L.total;
 }
 
@@ -407,7 +403,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   if (!h) return fail(CASA_ERR_INVALID, "handle is NULL");
   if (!mask || !vertex || !out_points) return fail(CASA_ERR_INVALID, "mask / vertex / out_points must not be NULL");
   Layout L;
-  int rc = make_layout(p, h->score_p, L);
+  int rc = make_layout(p, L);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   rc = ensure(&h->ws_mem, &h->ws_bytes, L.total);
@@ -434,15 +430,12 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   sa.fc = fc;
   sa.one = 1u;
   if (h->score_occ == 0) {
-    if (h->score_p == 4)
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<4>, kScoreThreads, 0));
-    else
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<3>, kScoreThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score, kScoreThreads, 0));
     if (h->score_occ < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
     const char* bps = getenv("CASA_SCORE_BPS");  // cap on resident scoring blocks per SM (experiments)
     if (bps && atoi(bps) >= 1 && atoi(bps) < h->score_occ) h->score_occ = atoi(bps);
   }
-  const void* score_fn = h->score_p == 4 ? (const void*)k_score<4> : (const void*)k_score<3>;
+  const void* score_fn = (const void*)k_score;
   const int refine_gx = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
   const int gather_gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
   const int vec4 = ((((size_t)d.hw * d.oc) & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
@@ -526,7 +519,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
   if (!mask_host || !vertex_host || !out_points_host) return fail(CASA_ERR_INVALID, "host buffers must not be NULL");
   Layout L;
-  int rc = make_layout(p, h->score_p, L);
+  int rc = make_layout(p, L);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t hw = (size_t)p->h * p->w;
@@ -638,7 +631,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   rp.round_hyp_num = 1; rp.max_iter = 1;
   rp.min_num = 0.f; rp.max_num = 3.0e38f; rp.inlier_thresh = 0.99f; rp.confidence = 0.99f;
   Layout L;
-  int rc = make_layout(&rp, h->score_p, L);
+  int rc = make_layout(&rp, L);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   const Dims& d = L.d;

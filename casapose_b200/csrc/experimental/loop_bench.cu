@@ -13,6 +13,9 @@
 //   6  PRMT + integer multiply-add accumulate (IMAD runs on the FMA pipe)
 //   7  no count, no minimum (4 FFMA + FADD + one XOR per pair keeps t alive): the floor of the formulation
 //   8  as 2 with 16 hypotheses per lane
+//   9  IMAD.HI.U32 count (hi32(t * 2) + n, FMA pipe) + FMNMX3 per pair
+//  10  as 6 with the trip unrolled to 4 pixels (loop overhead halved)
+//  11  IMAD.HI count, no minimum        12  IMAD.WIDE count (64-bit accumulator; wrong counts, rate probe only)
 // Prints TFLOP/s-equivalent (11 FLOP per unit, the accounting of SURVEY.md section 8d) and cycles per 32 units.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,7 +31,7 @@ __device__ __forceinline__ unsigned prmt_sign2(float a, float b) {  // 0xFFFF in
 }
 
 template <int V, int HPL>
-__global__ void __launch_bounds__(256) k_loop(float* out, int iters, float seedv, unsigned one) {
+__global__ void __launch_bounds__(256) k_loop(float* out, int iters, float seedv, unsigned one, unsigned two) {
   __shared__ float4 sA[8][kPix];
   __shared__ float2 sB[8][kPix];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,10 +101,15 @@ __global__ void __launch_bounds__(256) k_loop(float* out, int iters, float seedv
         } else if (V == 6) {
           nlo[i] = prmt_sign2(t[0][0], t[0][1]) * one + nlo[i];
           nlo[i + 1] = prmt_sign2(t[1][0], t[1][1]) * one + nlo[i + 1];
+        } else if (V == 9 || V == 11) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) nlo[i + j] = __umulhi(__float_as_uint(t[u][j]), two) + nlo[i + j];
         } else if (V == 7) {
           nlo[i] ^= __float_as_uint(t[0][0] + t[0][1]) ^ __float_as_uint(t[1][0] + t[1][1]);
         }
-        if (V != 3 && V != 7) {
+        if (V != 3 && V != 7 && V != 11) {
           mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t[0][0])), fabsf(t[0][1]));
           mn[i >> 1] = fminf(fminf(mn[i >> 1], fabsf(t[1][0])), fabsf(t[1][1]));
         }
@@ -134,7 +142,7 @@ static int run(const char* name, int sms, int blocks_per_sm, float* dout, double
   float best = 1e30f;
   for (int rep = 0; rep < 6; ++rep) {
     CK(cudaEventRecord(e0));
-    k_loop<V, HPL><<<blocks, 256>>>(dout, iters, 1e-9f, 1u);
+    k_loop<V, HPL><<<blocks, 256>>>(dout, iters, 1e-9f, 1u, 2u);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
@@ -175,5 +183,7 @@ int main(int argc, char** argv) {
   run<6, 8>("6 PRMT.sign + IMAD + FMNMX3/2", sms, bps, dout, peak, nullptr);
   run<7, 8>("7 no count, no min (floor)", sms, bps, dout, peak, nullptr);
   run<8, 16>("8 as 2, 16 hypotheses per lane", sms, bps, dout, peak, nullptr);
+  run<9, 8>("9 IMAD.HI count + FMNMX3/2", sms, bps, dout, peak, nullptr);
+  run<11, 8>("11 IMAD.HI count, no min", sms, bps, dout, peak, nullptr);
   return 0;
 }

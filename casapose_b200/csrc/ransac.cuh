@@ -168,7 +168,23 @@ __device__ __forceinline__ unsigned prmt_sign2(float a, float b) {
   return r;
 }
 
-constexpr int kHypPerLane = 8;
+// Build-time knobs of k_score, chosen by same-box A/B runs (profiles/r02_ab.txt).  The kernel is bound by dispatch
+// cycles, and the register allocation ptxas finds for the 440-instruction loop body moves the result by +-2 %:
+//   hypotheses per lane 8 (16: 128 registers, 2 blocks/SM, -8 %), 4 resident blocks/SM at 64 registers (3 at 80: -1 %),
+//   8 pixels per trip (4: -1 %, 2: spills at 64 registers), binary search over item_start (a 16-byte record per chunk
+//   removed the search but cost 2-4 % through a worse allocation of the loop).
+#ifndef CASA_HPL
+#define CASA_HPL 8
+#endif
+#ifndef CASA_SCORE_MINB
+#define CASA_SCORE_MINB 4
+#endif
+#ifndef CASA_PIX_UNROLL
+#define CASA_PIX_UNROLL 8
+#endif
+constexpr int kHypPerLane = CASA_HPL;             // hypotheses (and private counters) per lane of a scoring warp
+constexpr int kScoreMinBlocks = CASA_SCORE_MINB;  // resident 256-thread blocks per SM the kernel is compiled for
+constexpr int kPixUnroll = CASA_PIX_UNROLL;  // pixels per trip of the scoring loop
 
 // Exact inlier count of one hypothesis over pixels [t0, t0+npx) of a job, whole warp cooperating.
 __device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const float2* __restrict__ vd, int t0, int npx,
@@ -196,7 +212,7 @@ __device__ __noinline__ int exact_count(const uint32_t* __restrict__ pix, const 
 // run only when some lane has a correction (3 % of the flagged pairs).  The previous form (-DCASA_STAGE2_LOOP)
 // looped over the pixels with a branch per iteration and was latency-bound: 9.5 % of the kernel's instructions but
 // 28 % of its warp-stall samples (profiles/r01_k_score_source_regions.txt).
-__device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
+__device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int qb, int qe,
                                              float ax, float ay, float bx, float by, float ea, float eb, float kappa2,
                                              const float2* __restrict__ hfilt, int ha, int hb_ok,
                                              const uint32_t* __restrict__ pix, const float2* __restrict__ vd, int t0,
@@ -220,7 +236,7 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
     for (int k = 0; k < kChunk / 32; ++k) {
       const unsigned two = (inband >> (2 * k)) & 3u;
       const int q = k * 32 + lane;
-      if (two == 0u || q >= npx) continue;
+      if (two == 0u || q < qb || q >= qe) continue;
       const float4 A = cA[q];  // same instructions on the same operands as above: the same t, bit for bit
       const float2 B = cB[q];
       float pa, pb;
@@ -247,14 +263,14 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
   return make_int2(__reduce_add_sync(0xffffffffu, da), __reduce_add_sync(0xffffffffu, db));
 }
 #else
-__device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int npx,
+__device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, const float2* __restrict__ cB, int qb, int qe,
                                              float ax, float ay, float bx, float by, float ea, float eb, float kappa2,
                                              const float2* __restrict__ hfilt, int ha, int hb_ok,
                                              const uint32_t* __restrict__ pix, const float2* __restrict__ vd, int t0,
                                              float thr, unsigned& n_exact) {
   const int lane = threadIdx.x & 31;
   int da = 0, db = 0;
-  for (int q = lane; q < npx; q += 32) {
+  for (int q = qb + lane; q < qe; q += 32) {
     const float4 A = cA[q];
     const float2 B = cB[q];
     float pa, pb;
@@ -291,7 +307,7 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
 //    fractional bit), h' = fl(h - o) once per (hypothesis, chunk);
 //  * per pixel 6 coefficients in warp-private shared memory (24 B, broadcast LDS.128 + LDS.64):
 //        p = D hy' - E hx' - P0          (= d^ x (h - c))
-//        s = A0 - G hx' - H hy'          (= -k_lo d^ . (h - c))
+//        s = A0 - G hx' - H hy'          (= -k d^ . (h - c),  k = tan(theta0))
 //        t = |p| + s                     inlier <=> sign(t)
 //    5 FP32-pipe instructions per unit; the sign bits of a hypothesis pair are turned into two 16-bit fields by one
 //    PRMT and accumulated by one IMAD (FMA pipe) — every negative unit adds 0xFFFF to its field, decoded after the
@@ -301,14 +317,15 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
 //  * min |t| per hypothesis pair is compared with B = c1 (|h'| + R): if min|t| >= B every sign in the
 //    chunk is provably the reference's verdict (predicate.cuh / DESIGN.md); otherwise band_adjust()
 //    finds the (rare) units that need the exact predicate.
-template <int MINB>
-__global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
+__global__ void __launch_bounds__(kScoreThreads, kScoreMinBlocks) k_score(ScoreArgs a) {
   __shared__ float4 sA[kScoreWarps][kChunk];  // (D, -E, -P0, A0)
   __shared__ float2 sB[kScoreWarps][kChunk];  // (-G, -H)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hn = a.d.hn;
   const int n_items = a.ws.ctrl[CTRL_NITEMS];
   const int n_groups = (hn + 32 * kHypPerLane - 1) / (32 * kHypPerLane);
+  const int n_full = max(0, n_items - (int)(gridDim.x * kScoreWarps));  // items before the split tail
+  const int n_virtual = n_full + (n_items - n_full) * n_groups;
   float4* cA = sA[warp];
   float2* cB = sB[warp];
   const float qnan = __int_as_float(0x7fc00000);
@@ -317,9 +334,18 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     int item = 0;
     if (lane == 0) item = atomicAdd(&a.ws.ctrl[CTRL_WORK], 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= n_items) break;
-    // item -> (job, chunk, keypoint): binary search in the per-job prefix of work items (keypoint innermost,
-    // so the 9 items that share a chunk's pixels are handed out back to back)
+    if (item >= n_virtual) break;
+    // The last `n_items - n_full` items are handed out one hypothesis group at a time, so that the tail of the
+    // persistent grid is a group (half an item at 512 hypotheses) instead of an item.  (Splitting the pixels of the
+    // tail items as well made the main loop's range variable and the whole kernel 1.7 % slower: profiles/r02_ab.txt.)
+    int g_begin = 0, g_end = n_groups;
+    if (item >= n_full) {
+      const int j = item - n_full;
+      item = n_full + j / n_groups;
+      g_begin = j - (j / n_groups) * n_groups;
+      g_end = g_begin + 1;
+    }
+    // item -> (job, chunk, keypoint): binary search in the per-job prefix of work items
     int lo = 0, hi = a.d.J;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -334,6 +360,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     const float2* vd = job_dirs(a.ws, a.d, img, job, tn, v);
     const int t0 = chunk * kChunk;
     const int npx = min(kChunk, tn - t0);
+    const bool first_part = g_begin == 0;  // the exact list and the exact whole-chunk path run once per item
 
     // pixels of the chunk (4 per lane), bounding box, origin
     int px[kChunk / 32], py[kChunk / 32];
@@ -382,6 +409,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     int* gc = a.ws.counts + hoff;
     const float2* htrue = a.ws.hyp_true + hoff;
     if (a.fc.fast_ok == 0 || weird) {  // rare: whole chunk with the exact predicate
+      if (!first_part) continue;
       for (int h = 0; h < hn; ++h) {
         const float2 hp = htrue[h];
         const int c = exact_count(pix, vd, t0, npx, hp.x, hp.y, a.fc.thr);
@@ -392,7 +420,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
     }
 
     const float2* hfilt = a.ws.hyp_filt + hoff;
-    for (int g = 0; g < n_groups; ++g) {
+    for (int g = g_begin; g < g_end; ++g) {
       float hx[kHypPerLane], hy[kHypPerLane], mn[kHypPerLane / 2];
       unsigned acc[kHypPerLane / 2];  // two 16-bit sign counters per hypothesis pair (a 128-pixel chunk cannot overflow them)
 #pragma unroll
@@ -408,7 +436,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
         mn[i] = 3.0e38f;
         acc[i] = 0u;
       }
-#pragma unroll 2
+#pragma unroll(kPixUnroll)
       for (int q = 0; q < npx; ++q) {
         const float4 A = cA[q];
         const float2 B = cB[q];
@@ -452,7 +480,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
             const float2 pb = hb_ok ? hfilt[ha + 32] : make_float2(qnan, qnan);
             const float ax = pa.x - ox, ay = pa.y - oy, bx = pb.x - ox, by = pb.y - oy;  // same h' as the main loop
             const float ea = a.fc.e1 * (oct_norm(ax, ay) + rr), eb = a.fc.e1 * (oct_norm(bx, by) + rr);
-            const int2 dd = band_adjust2(cA, cB, npx, ax, ay, bx, by, ea, eb, a.fc.kappa2, hfilt, ha, hb_ok, pix, vd,
+            const int2 dd = band_adjust2(cA, cB, 0, npx, ax, ay, bx, by, ea, eb, a.fc.kappa2, hfilt, ha, hb_ok, pix, vd,
                                          t0, a.fc.thr, n_exact);
             if (lane == 0) {
               if (dd.x) atomicAdd(&gc[ha], dd.x);
@@ -464,7 +492,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) k_score(ScoreArgs a) {
       }
     }
     // hypotheses the filter cannot take (exact list)
-    const int nlist = a.ws.n_exact[job * a.d.vn + v];
+    const int nlist = first_part ? a.ws.n_exact[job * a.d.vn + v] : 0;
     for (int k = 0; k < nlist; ++k) {
       const int h = a.ws.exact_list[hoff + k];
       const float2 hp = htrue[h];

@@ -78,6 +78,8 @@ EXPORTS = {
                            C.c_void_p]),
     "casa_pose_errors": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "casa_set_async": (C.c_int, [C.c_void_p, C.c_int]),
+    "casa_sync": (C.c_int, [C.c_void_p]),
     "casa_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "casa_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "casa_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
@@ -139,9 +141,12 @@ def check(rc):
         raise CasaError("casapose_b200 error %d: %s" % (rc, lib().casa_last_error().decode()))
 
 
-def handle(device):
-    """One library handle per (device, thread)."""
-    key = (int(device), threading.get_ident())
+def handle(device, stream=0):
+    """One library handle per (device, thread, CUDA stream).
+
+    A handle owns one workspace and leaves refinement / solve running when a call returns, so two streams must
+    never share one (include/casapose_b200.h: one handle per stream)."""
+    key = (int(device), threading.get_ident(), int(stream or 0))
     h = _handles.get(key)
     if h is None:
         hp = C.c_void_p()
@@ -149,6 +154,16 @@ def handle(device):
         h = hp
         _handles[key] = h
     return h
+
+
+def set_async(device, enable, stream=0):
+    """Asynchronous calls on this (device, thread, stream) handle: consecutive votes queue back to back on the GPU;
+    `sync(device)` waits for them and raises the first error any of them hit (casa_set_async / casa_sync)."""
+    check(lib().casa_set_async(handle(device, stream), 1 if enable else 0))
+
+
+def sync(device, stream=0):
+    check(lib().casa_sync(handle(device, stream)))
 
 
 def status_names(word):

@@ -35,6 +35,17 @@ static int fail(int code, const char* fmt, ...) {
       return fail(CASA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// Read-back slot of one call: the loop state, the statistics and the events of a call live in their own slot of a ring,
+// so that asynchronous callers can queue calls back to back and collect them later (casa_sync / casa_get_timing).
+struct CallSlot {
+  int* ctrl = nullptr;                   // CTRL_WORDS ints, page-locked
+  unsigned long long* stats = nullptr;   // 4 words, page-locked
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_round = nullptr;
+  int timed = 0;
+  int64_t base_launches = 0, round_launches = 0;
+};
+constexpr int kCallSlots = 256;
+
 struct casa_handle {
   int device = 0;
   int sm_count = 148;
@@ -54,9 +65,18 @@ struct casa_handle {
   double score_ms = 0.0;
   int64_t score_launches = 0;
   uint64_t stats[4] = {0, 0, 0, 0};
+  int64_t rounds_total = 0, launches_total = 0;
   unsigned long long* pinned_stats = nullptr;  // 4 words, page-locked
   int score_occ = 0;
   int use_graph = 1;
+  CallSlot slots[kCallSlots];
+  char* slot_mem = nullptr;       // page-locked backing store of the slots' read-back buffers
+  int64_t slot_head = 0, slot_tail = 0;  // calls issued / calls collected (pending = head - tail)
+  cudaStream_t last_stream = nullptr;
+  const void* clean_ctrl = nullptr;  // address of the ctrl / stats words the previous vote's graph left zeroed (layouts move them)
+  int async_mode = 0;             // 1: casa_ransac_vote returns without waiting for the loop state (casa_sync collects errors)
+  uint32_t* sticky = nullptr;     // device word: OR of the status words of every call since the last casa_sync
+  uint32_t* pinned_sticky = nullptr;
   std::vector<struct casa_graph*> graphs;
 };
 
@@ -64,7 +84,9 @@ struct casa_graph {
   uint64_t key = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  std::vector<cudaGraphNode_t> knodes;  // kernel nodes in list order
+  std::vector<cudaGraphNode_t> knodes;  // kernel nodes in list order (top level and WHILE body alike)
+  cudaGraphConditionalHandle cond = 0;  // condition of the graph's WHILE node (0: the list has no loop)
+  cudaGraphNode_t ev0_node = nullptr, ev1_node = nullptr, evr_node = nullptr, ctrl_node = nullptr, stats_node = nullptr;
 };
 
 extern "C" int casa_version(void) { return CASA_VERSION; }
@@ -85,12 +107,24 @@ extern "C" int casa_create(int device, casa_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaHostAlloc((void**)&h->pinned, CTRL_WORDS * sizeof(int), cudaHostAllocDefault));
   CUDA_TRY(cudaHostAlloc((void**)&h->pinned_stats, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc((void**)&h->pinned_sticky, sizeof(uint32_t), cudaHostAllocDefault));
+  CUDA_TRY(cudaMalloc((void**)&h->sticky, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->sticky, 0, sizeof(uint32_t)));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->part_ev[i], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_round, cudaEventDisableTiming));
+  CUDA_TRY(cudaHostAlloc((void**)&h->slot_mem, (size_t)kCallSlots * 64, cudaHostAllocDefault));
+  for (int i = 0; i < kCallSlots; ++i) {
+    CallSlot& c = h->slots[i];
+    c.ctrl = (int*)(h->slot_mem + (size_t)i * 64);
+    c.stats = (unsigned long long*)(h->slot_mem + (size_t)i * 64 + 32);
+    CUDA_TRY(cudaEventCreate(&c.ev0));
+    CUDA_TRY(cudaEventCreate(&c.ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&c.ev_round, cudaEventDisableTiming));
+  }
   if (getenv("CASA_NO_GRAPH")) h->use_graph = 0;
   *out = h;
   return CASA_OK;
@@ -109,6 +143,8 @@ extern "C" int casa_destroy(casa_handle* h) {
   if (h->metric_mem) cudaFree(h->metric_mem);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->pinned_stats) cudaFreeHost(h->pinned_stats);
+  if (h->pinned_sticky) cudaFreeHost(h->pinned_sticky);
+  if (h->sticky) cudaFree(h->sticky);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < 8; ++i)
@@ -116,6 +152,12 @@ extern "C" int casa_destroy(casa_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_round) cudaEventDestroy(h->ev_round);
+  for (int i = 0; i < kCallSlots; ++i) {
+    if (h->slots[i].ev0) cudaEventDestroy(h->slots[i].ev0);
+    if (h->slots[i].ev1) cudaEventDestroy(h->slots[i].ev1);
+    if (h->slots[i].ev_round) cudaEventDestroy(h->slots[i].ev_round);
+  }
+  if (h->slot_mem) cudaFreeHost(h->slot_mem);
   delete h;
   return CASA_OK;
 }
@@ -190,8 +232,8 @@ int make_layout(const casa_ransac_params* p, Layout& L) {
   L.off_rtile_start = bump(cur, (J + 1) * 4);
   L.off_rtile_job = bump(cur, (size_t)d.max_rtiles * 4);
   L.off_ctrl = bump(cur, CTRL_WORDS * 4);
+  L.off_stats = bump(cur, 4 * 8);  // directly behind ctrl: one memset node clears both (run_graph: STEP_CLEAR)
   L.off_partial = bump(cur, (size_t)d.max_rtiles * d.vn * 5 * 8);
-  L.off_stats = bump(cur, 4 * 8);
   L.total = cur;
   return CASA_OK;
 }
@@ -253,7 +295,7 @@ extern "C" size_t casa_ransac_workspace_bytes(const casa_ransac_params* p) {
 // ---- as a CUDA graph whose kernel-node parameters are patched per call (CUDA graphs instead of launch gaps).
 namespace {
 
-enum StepKind { STEP_KERNEL, STEP_EV0, STEP_EV1, STEP_READBACK };
+enum StepKind { STEP_KERNEL, STEP_EV0, STEP_EV1, STEP_READBACK, STEP_CLEAR, STEP_WHILE_BEGIN, STEP_WHILE_END };
 
 struct Step {
   StepKind kind = STEP_KERNEL;
@@ -264,6 +306,19 @@ struct Step {
   size_t off[8];
   size_t used = 0;
   int n = 0;
+  int cond_arg = -1;  // index of the argument that receives the graph's WHILE condition handle (k_update)
+  // graph topology: 0 = main chain; 1 = opens a side branch off the main chain's last node; 2 = continues the side
+  // branch.  join: this main-chain step also waits for the side branch (which ends there).
+  int side = 0;
+  bool join = false;
+  Step& on_side(int v) {
+    side = v;
+    return *this;
+  }
+  Step& joins() {
+    join = true;
+    return *this;
+  }
   template <class T>
   Step& arg(const T& v) {
     used = (used + alignof(T) - 1) & ~(alignof(T) - 1);
@@ -271,6 +326,13 @@ struct Step {
     off[n++] = used;
     used += sizeof(T);
     return *this;
+  }
+  Step& cond() {  // placeholder for the condition handle, filled in by run_graph / run_direct
+    cond_arg = n;
+    return arg((unsigned long long)0);
+  }
+  void set_cond(unsigned long long v) {
+    if (cond_arg >= 0) memcpy(buf + off[cond_arg], &v, sizeof(v));
   }
   void ptrs(void** out) {
     for (int i = 0; i < n; ++i) out[i] = buf + off[i];
@@ -286,9 +348,10 @@ Step kstep(const void* func, dim3 grid, dim3 block, size_t smem = 0) {
   return s;
 }
 
-Step special(StepKind k) {
+Step special(StepKind k, int side = 0) {
   Step s;
   s.kind = k;
+  s.side = side;
   return s;
 }
 
@@ -300,30 +363,61 @@ uint64_t fnv(uint64_t hsh, const void* p, size_t n) {
 
 }  // namespace
 
+static int launch_step(Step& s, cudaStream_t st) {
+  void* args[8];
+  s.ptrs(args);
+  CUDA_TRY(cudaLaunchKernel(s.func, s.grid, s.block, args, s.smem, st));
+  return CASA_OK;
+}
 
-static int run_direct(casa_handle* h, std::vector<Step>& steps, const WS& ws, cudaStream_t st) {
-  for (Step& s : steps) {
+// Direct launches (CASA_NO_GRAPH=1; debugging and the sanitizer runs): the WHILE section is driven from the host,
+// one 32-byte read-back per round — the reference's data-dependent `while` (:318) as the first version ran it.
+static int run_direct(casa_handle* h, std::vector<Step>& steps, const WS& ws, cudaStream_t st, CallSlot* slot = nullptr) {
+  for (size_t i = 0; i < steps.size(); ++i) {
+    Step& s = steps[i];
     switch (s.kind) {
       case STEP_KERNEL: {
-        void* args[8];
-        s.ptrs(args);
-        CUDA_TRY(cudaLaunchKernel(s.func, s.grid, s.block, args, s.smem, st));
+        int rc = launch_step(s, st);
+        if (rc) return rc;
         break;
       }
-      case STEP_EV0: CUDA_TRY(cudaEventRecord(h->ev0, st)); break;
-      case STEP_EV1: CUDA_TRY(cudaEventRecord(h->ev1, st)); break;
-      case STEP_READBACK:
-        // the reference's data-dependent `while` (:318): one 32-byte read-back per round
-        CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h->pinned_stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(h->ev_round, st));
+      case STEP_CLEAR:
+        CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
         break;
+      case STEP_EV0: CUDA_TRY(cudaEventRecord(slot->ev0, st)); break;
+      case STEP_EV1: CUDA_TRY(cudaEventRecord(slot->ev1, st)); break;
+      case STEP_READBACK:
+        CUDA_TRY(cudaMemcpyAsync(slot->ctrl, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(slot->stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(slot->ev_round, st));
+        break;
+      case STEP_WHILE_BEGIN: {
+        size_t end = i + 1;
+        while (end < steps.size() && steps[end].kind != STEP_WHILE_END) ++end;
+        for (;;) {
+          CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+          CUDA_TRY(cudaStreamSynchronize(st));
+          if (h->pinned[CTRL_NACTIVE] == 0) break;
+          for (size_t k = i + 1; k < end; ++k) {
+            int rc = launch_step(steps[k], st);
+            if (rc) return rc;
+          }
+        }
+        i = end;
+        break;
+      }
+      case STEP_WHILE_END: break;
     }
   }
   return CASA_OK;
 }
 
-static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cudaStream_t st) {
+// The whole call as ONE CUDA graph: kernel nodes, the clear / read-back nodes, and a conditional WHILE node whose
+// body (the RANSAC rounds after the first) repeats on the device until k_update sets the condition to 0.  Graphs are
+// cached per launch shape; per call only the kernel-node parameters are patched (cudaGraphExecKernelNodeSetParams
+// also reaches the nodes of the WHILE body).
+static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cudaStream_t st, CallSlot* slot = nullptr) {
   uint64_t key = 1469598103934665603ull;
   for (const Step& s : steps) {
     key = fnv(key, &s.kind, sizeof(s.kind));
@@ -332,41 +426,99 @@ static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cud
     key = fnv(key, &s.block, sizeof(s.block));
     key = fnv(key, &s.smem, sizeof(s.smem));
   }
-  key = fnv(key, &ws.ctrl, sizeof(ws.ctrl));  // the read-back nodes carry workspace addresses
+  key = fnv(key, &ws.ctrl, sizeof(ws.ctrl));  // the clear / read-back nodes carry workspace addresses
   casa_graph* g = nullptr;
   for (casa_graph* c : h->graphs)
     if (c->key == key) g = c;
+  auto kparams = [](Step& s, void** args, cudaKernelNodeParams& kp) {
+    s.ptrs(args);
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)s.func;
+    kp.gridDim = s.grid;
+    kp.blockDim = s.block;
+    kp.sharedMemBytes = (unsigned)s.smem;
+    kp.kernelParams = args;
+  };
   if (!g) {
     g = new casa_graph();
     g->key = key;
     CUDA_TRY(cudaGraphCreate(&g->graph, 0));
-    cudaGraphNode_t prev = nullptr;
-    auto deps = [&]() { return prev ? &prev : nullptr; };
+    bool has_loop = false;
+    for (const Step& s : steps) has_loop |= s.kind == STEP_WHILE_BEGIN;
+    if (has_loop) CUDA_TRY(cudaGraphConditionalHandleCreate(&g->cond, g->graph, 0, cudaGraphCondAssignDefault));
+    cudaGraph_t cur = g->graph;
+    cudaGraphNode_t prev = nullptr, side_prev = nullptr, loop_node = nullptr;
     for (Step& s : steps) {
       cudaGraphNode_t node = nullptr;
-      const size_t nd = prev ? 1 : 0;
-      if (s.kind == STEP_KERNEL) {
-        void* args[8];
-        s.ptrs(args);
-        cudaKernelNodeParams kp;
-        memset(&kp, 0, sizeof(kp));
-        kp.func = (void*)s.func;
-        kp.gridDim = s.grid;
-        kp.blockDim = s.block;
-        kp.sharedMemBytes = (unsigned)s.smem;
-        kp.kernelParams = args;
-        CUDA_TRY(cudaGraphAddKernelNode(&node, g->graph, deps(), nd, &kp));
-        g->knodes.push_back(node);
-      } else if (s.kind == STEP_EV0 || s.kind == STEP_EV1) {
-        CUDA_TRY(cudaGraphAddEventRecordNode(&node, g->graph, deps(), nd, s.kind == STEP_EV0 ? h->ev0 : h->ev1));
+      cudaGraphNode_t deps[2];
+      size_t nd = 0;
+      if (s.side == 2) {
+        if (side_prev) deps[nd++] = side_prev;
       } else {
-        CUDA_TRY(cudaGraphAddMemcpyNode1D(&node, g->graph, deps(), nd, h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost));
-        prev = node;
-        CUDA_TRY(cudaGraphAddMemcpyNode1D(&node, g->graph, &prev, 1, h->pinned_stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        prev = node;
-        CUDA_TRY(cudaGraphAddEventRecordNode(&node, g->graph, &prev, 1, h->ev_round));
+        if (prev) deps[nd++] = prev;
+        if (s.join && side_prev) deps[nd++] = side_prev;
       }
-      prev = node;
+      cudaGraphNode_t* dep = nd ? deps : nullptr;
+      switch (s.kind) {
+        case STEP_KERNEL: {
+          s.set_cond((unsigned long long)g->cond);
+          void* args[8];
+          cudaKernelNodeParams kp;
+          kparams(s, args, kp);
+          CUDA_TRY(cudaGraphAddKernelNode(&node, cur, dep, nd, &kp));
+          g->knodes.push_back(node);
+          break;
+        }
+        case STEP_EV0:
+        case STEP_EV1:
+          CUDA_TRY(cudaGraphAddEventRecordNode(&node, cur, dep, nd, s.kind == STEP_EV0 ? slot->ev0 : slot->ev1));
+          (s.kind == STEP_EV0 ? g->ev0_node : g->ev1_node) = node;
+          break;
+        case STEP_CLEAR: {  // ctrl and stats are adjacent in the workspace: one memset node
+          cudaMemsetParams mp;
+          memset(&mp, 0, sizeof(mp));
+          mp.dst = ws.ctrl;
+          mp.elementSize = 4;
+          mp.width = ((char*)ws.stats - (char*)ws.ctrl) / 4 + 8;
+          mp.height = 1;
+          mp.value = 0;
+          CUDA_TRY(cudaGraphAddMemsetNode(&node, cur, dep, nd, &mp));
+          break;
+        }
+        case STEP_READBACK: {
+          CUDA_TRY(cudaGraphAddMemcpyNode1D(&node, cur, dep, nd, slot->ctrl, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost));
+          g->ctrl_node = node;
+          cudaGraphNode_t p2 = node;
+          CUDA_TRY(cudaGraphAddMemcpyNode1D(&node, cur, &p2, 1, slot->stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+          g->stats_node = p2 = node;
+          CUDA_TRY(cudaGraphAddEventRecordNode(&node, cur, &p2, 1, slot->ev_round));
+          g->evr_node = node;
+          break;
+        }
+        case STEP_WHILE_BEGIN: {
+          cudaGraphNodeParams cp = {};
+          cp.type = cudaGraphNodeTypeConditional;
+          cp.conditional.handle = g->cond;
+          cp.conditional.type = cudaGraphCondTypeWhile;
+          cp.conditional.size = 1;
+          CUDA_TRY(cudaGraphAddNode(&loop_node, cur, dep, nd, &cp));
+          cur = cp.conditional.phGraph_out[0];
+          prev = nullptr;
+          side_prev = nullptr;
+          continue;
+        }
+        case STEP_WHILE_END:
+          cur = g->graph;
+          prev = loop_node;
+          side_prev = nullptr;
+          continue;
+      }
+      if (s.side == 0) {
+        prev = node;
+        if (s.join) side_prev = nullptr;
+      } else {
+        side_prev = node;
+      }
     }
     CUDA_TRY(cudaGraphInstantiate(&g->exec, g->graph, 0));
     if (h->graphs.size() >= 16) {  // tiny cache: drop the oldest shape
@@ -381,20 +533,64 @@ static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cud
     size_t k = 0;
     for (Step& s : steps) {
       if (s.kind != STEP_KERNEL) continue;
+      s.set_cond((unsigned long long)g->cond);
       void* args[8];
-      s.ptrs(args);
       cudaKernelNodeParams kp;
-      memset(&kp, 0, sizeof(kp));
-      kp.func = (void*)s.func;
-      kp.gridDim = s.grid;
-      kp.blockDim = s.block;
-      kp.sharedMemBytes = (unsigned)s.smem;
-      kp.kernelParams = args;
+      kparams(s, args, kp);
       CUDA_TRY(cudaGraphExecKernelNodeSetParams(g->exec, g->knodes[k++], &kp));
+    }
+    if (slot) {  // this call's read-back slot
+      if (g->ev0_node) CUDA_TRY(cudaGraphExecEventRecordNodeSetEvent(g->exec, g->ev0_node, slot->ev0));
+      if (g->ev1_node) CUDA_TRY(cudaGraphExecEventRecordNodeSetEvent(g->exec, g->ev1_node, slot->ev1));
+      if (g->evr_node) CUDA_TRY(cudaGraphExecEventRecordNodeSetEvent(g->exec, g->evr_node, slot->ev_round));
+      if (g->ctrl_node)
+        CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(g->exec, g->ctrl_node, slot->ctrl, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost));
+      if (g->stats_node)
+        CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(g->exec, g->stats_node, slot->stats, ws.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
   }
   CUDA_TRY(cudaGraphLaunch(g->exec, st));
   return CASA_OK;
+}
+
+// Collects every call that has been issued but not looked at yet: waits for its loop state (not for its refinement /
+// solve), accumulates its statistics and timing into the handle and returns the first error any of them raised.
+// A synchronous call collects itself; asynchronous calls are collected by casa_sync / casa_get_timing / when the
+// ring of read-back slots is full.
+static void reset_totals(casa_handle* h) {
+  h->score_ms = 0.0;
+  h->score_launches = 0;
+  h->rounds_total = 0;
+  h->launches_total = 0;
+  for (int k = 0; k < 4; ++k) h->stats[k] = 0;
+}
+
+static int collect(casa_handle* h) {
+  int first_rc = CASA_OK;
+  while (h->slot_tail < h->slot_head) {
+    CallSlot& c = h->slots[h->slot_tail % kCallSlots];
+    CUDA_TRY(cudaEventSynchronize(c.ev_round));
+    ++h->slot_tail;
+    const int rounds = c.ctrl[CTRL_ROUND];
+    h->score_launches += c.timed ? 1 : 0;
+    h->rounds_total += rounds;
+    h->last_launches = c.base_launches + (int64_t)(rounds > 1 ? rounds - 1 : 0) * c.round_launches;
+    h->launches_total += h->last_launches;
+    if (c.timed) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+      h->score_ms += ms;  // k_score of round 0 (later rounds run inside the WHILE body, which cannot hold event nodes)
+    }
+    for (int k = 0; k < 4; ++k) h->stats[k] += c.stats[k];
+    h->last_status = (uint32_t)c.ctrl[CTRL_STATUS];
+    if (first_rc == CASA_OK) {
+      if (h->last_status & CASA_STATUS_PIX_OVERFLOW)
+        first_rc = fail(CASA_ERR_WORKSPACE, "pixel lists exceed pix_capacity (mask is not one-hot?); retry with a larger pix_capacity");
+      else if (h->last_status & CASA_STATUS_IDX_RANGE)
+        first_rc = fail(CASA_ERR_INPUT, "caller-supplied idxs outside [0, tn)");
+    }
+  }
+  return first_rc;
 }
 
 static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const float* mask, int mask_is_seg,
@@ -406,24 +602,26 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   int rc = make_layout(p, L);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->ws_bytes < L.total) h->clean_ctrl = nullptr;
   rc = ensure(&h->ws_mem, &h->ws_bytes, L.total);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->slot_head - h->slot_tail >= kCallSlots) {  // the ring of read-back slots is full: collect the queued calls
+    rc = collect(h);
+    if (rc) return rc;
+  }
+  if (!h->async_mode) reset_totals(h);  // synchronous calls report per-call statistics
+  CallSlot* slot = &h->slots[h->slot_head % kCallSlots];
+  h->last_stream = st;
   casa_ransac_debug dbg;
   memset(&dbg, 0, sizeof(dbg));
   if (debug) dbg = *debug;
   const Dims& d = L.d;
   WS ws = make_ws(L, h->ws_mem, true);
   const FilterConsts fc = filter_consts(p->inlier_thresh, p->force_exact);
-  int64_t launches = 0;
 
-  CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
-  CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
   // debug copy of the pixel lists takes the whole [b][cap] buffer: define the unused tail (debug calls only)
   if (dbg.pix) CUDA_TRY(cudaMemsetAsync(ws.pix, 0, (size_t)d.b * d.cap * 4, st));
-  h->score_ms = 0.0;
-  h->score_launches = 0;
-
   ScoreArgs sa;
   sa.ws = ws;
   sa.d = d;
@@ -439,55 +637,77 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   const int refine_gx = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
   const int gather_gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
   const int vec4 = ((((size_t)d.hw * d.oc) & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
+  const int plan_threads = d.J > 256 ? 1024 : 256;
 
-  for (int rnd = 0; rnd < d.max_iter; ++rnd) {
-    std::vector<Step> steps;
-    steps.reserve(20);
-    if (rnd == 0) {  // K1: compaction and the direction gather
-      if (mask_is_seg)
-        steps.push_back(kstep((const void*)k_seg_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d));
-      else
-        steps.push_back(kstep((const void*)k_mask_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d).arg(vec4));
-      steps.push_back(kstep((const void*)k_scan_tiles, d.J, 128).arg(ws).arg(d));
-      steps.push_back(kstep((const void*)k_job_table, (d.b + 63) / 64, 64).arg(ws).arg(d));
-      steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
-      if ((float)d.hw > p->max_num) steps.push_back(kstep((const void*)k_cap_filter, d.J, 1024).arg(ws).arg(d).arg(selection));
-      steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gather_gx, d.J), 256)
-                          .arg(vertex).arg(ws).arg(d));
-    }
-    steps.push_back(kstep((const void*)k_plan, 1, 256).arg(ws).arg(d).arg(rnd));
-    steps.push_back(kstep((const void*)k_hypgen, dim3((d.hn * d.vn + 255) / 256, d.J), 256).arg(ws).arg(d).arg(fc).arg(idxs).arg(rnd).arg(dbg.hyps));
-    if (h->timing) steps.push_back(special(STEP_EV0));
-    steps.push_back(kstep(score_fn, h->sm_count * h->score_occ, kScoreThreads).arg(sa));
-    if (h->timing) steps.push_back(special(STEP_EV1));
-    steps.push_back(kstep((const void*)k_update, d.J, 32 * d.vn).arg(ws).arg(d).arg(rnd).arg(dbg));
-    // Refinement and solve are queued BEFORE the host waits for the loop state, so in the common single-round
-    // case the GPU never idles on the round trip; if another round is needed they simply run again after it.
-    steps.push_back(special(STEP_READBACK));
-    steps.push_back(kstep((const void*)k_refine, dim3(refine_gx, d.vn), 256).arg(ws).arg(d).arg(fc));
-    steps.push_back(kstep((const void*)k_solve, d.J, 32).arg(ws).arg(d).arg(out_points).arg(dbg));
-    for (const Step& s : steps) launches += s.kind == STEP_KERNEL;
-    rc = (rnd == 0 && h->use_graph) ? run_graph(h, steps, ws, st) : run_direct(h, steps, ws, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventSynchronize(h->ev_round));  // the host waits for the loop state only, not for refine/solve
-    ++h->score_launches;
-    if (h->timing) {
-      float ms = 0.f;
-      CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-      h->score_ms += ms;
-    }
-    for (int k = 0; k < 4; ++k) h->stats[k] = h->pinned_stats[k];
-    if (h->pinned[CTRL_NACTIVE] == 0) break;
+  // The launch list of the whole call.  Round 0 is spelled out (it carries the timing events, which a WHILE body
+  // may not hold); rounds >= 1 are the body of a device-driven WHILE (k_update publishes the round index and the
+  // condition), entered only when some job has not met the stop test (:344-347).  Refinement and solve run once,
+  // after the loop; the 32-byte loop state and the statistics are read back in front of them, so a synchronous
+  // caller learns the status while the GPU is still busy.
+  std::vector<Step> steps;
+  steps.reserve(32);
+  int64_t base_launches = 0, round_launches = 0;
+  // ctrl / stats are clean when the previous call on this workspace was a vote (its graph clears them at its end);
+  // after anything else (first call, re-allocation, the LS layer) they are cleared in front of the graph.
+  if (h->clean_ctrl != (const void*)ws.ctrl) {
+    CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
   }
+  if (mask_is_seg)
+    steps.push_back(kstep((const void*)k_seg_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d));
+  else
+    steps.push_back(kstep((const void*)k_mask_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d).arg(vec4));
+  steps.push_back(kstep((const void*)k_scan_tiles, d.J, 128).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_job_table, (d.b + 63) / 64, 64).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
+  if ((float)d.hw > p->max_num) steps.push_back(kstep((const void*)k_cap_filter, d.J, 1024).arg(ws).arg(d).arg(selection));
+  // round 0's plan only needs the job table: it runs beside the direction gather (side branch, joined by k_hypgen)
+  steps.push_back(kstep((const void*)k_plan, 1, plan_threads).arg(ws).arg(d).arg((int)0).on_side(1));
+  steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gather_gx, d.J), 256)
+                      .arg(vertex).arg(ws).arg(d));
+  for (int part = 0; part < 2; ++part) {  // part 0: round 0; part 1: the WHILE body (rnd = -1: read ctrl[CTRL_ROUND])
+    const int rnd = part == 0 ? 0 : -1;
+    if (part == 1) {
+      if (d.max_iter < 2) break;
+      steps.push_back(special(STEP_WHILE_BEGIN));
+      steps.push_back(kstep((const void*)k_plan, 1, plan_threads).arg(ws).arg(d).arg(rnd));
+    }
+    const size_t n0 = steps.size();
+    Step hg = kstep((const void*)k_hypgen, dim3((d.hn * d.vn + 255) / 256, d.J), 256).arg(ws).arg(d).arg(fc).arg(idxs).arg(rnd).arg(dbg.hyps);
+    if (part == 0) hg.joins();
+    steps.push_back(hg);
+    // the timing events hang off the chain as leaves: ev0 fires when k_hypgen is done, ev1 when k_score is done
+    if (part == 0 && h->timing) steps.push_back(special(STEP_EV0, 1));
+    steps.push_back(kstep(score_fn, h->sm_count * h->score_occ, kScoreThreads).arg(sa));
+    if (part == 0 && h->timing) steps.push_back(special(STEP_EV1, 1));
+    steps.push_back(kstep((const void*)k_update, d.J, 32 * d.vn).arg(ws).arg(d).arg(rnd).arg(dbg).cond().arg(h->sticky));
+    if (part == 1) {
+      for (size_t k = n0 - 1; k < steps.size(); ++k) round_launches += steps[k].kind == STEP_KERNEL;
+      steps.push_back(special(STEP_WHILE_END));
+    }
+  }
+  // the read-back of the loop state (and the clearing of ctrl / stats for the next call) is a side branch: refinement
+  // and solve do not wait for the copy engine
+  steps.push_back(special(STEP_READBACK, 1));
+  steps.push_back(special(STEP_CLEAR, 2));
+  steps.push_back(kstep((const void*)k_refine, dim3(refine_gx, d.vn), 256).arg(ws).arg(d).arg(fc));
+  steps.push_back(kstep((const void*)k_solve, d.J, 32).arg(ws).arg(d).arg(out_points).arg(dbg));
+  for (const Step& s2 : steps) base_launches += s2.kind == STEP_KERNEL;
+  base_launches -= round_launches;  // the body's kernels are counted per executed round below
+  slot->timed = h->timing;
+  slot->base_launches = base_launches;
+  slot->round_launches = round_launches;
+  rc = h->use_graph ? run_graph(h, steps, ws, st, slot) : run_direct(h, steps, ws, st, slot);
+  if (rc) return rc;
+  ++h->slot_head;
+  h->clean_ctrl = ws.ctrl;
   CUDA_TRY(cudaGetLastError());
   if (dbg.pix) CUDA_TRY(cudaMemcpyAsync(dbg.pix, ws.pix, (size_t)d.b * d.cap * 4, cudaMemcpyDeviceToDevice, st));
-  if (dbg.stats) CUDA_TRY(cudaMemcpyAsync(dbg.stats, ws.stats, 4 * 8, cudaMemcpyDeviceToDevice, st));
-  h->last_status = (uint32_t)h->pinned[CTRL_STATUS];
-  h->last_launches = launches;
-  if (h->last_status & CASA_STATUS_PIX_OVERFLOW)
-    return fail(CASA_ERR_WORKSPACE, "pixel lists exceed pix_capacity=%d (mask is not one-hot?); retry with a larger pix_capacity", d.cap);
-  if (h->last_status & CASA_STATUS_IDX_RANGE) return fail(CASA_ERR_INPUT, "caller-supplied idxs outside [0, tn)");
-  return CASA_OK;
+  if (h->async_mode && !dbg.stats) return CASA_OK;  // status, statistics and timing are collected by casa_sync()
+  rc = collect(h);
+  // debug copy of the statistics: from the call's read-back slot (the workspace words are cleared by the graph)
+  if (dbg.stats) CUDA_TRY(cudaMemcpyAsync(dbg.stats, slot->stats, 4 * 8, cudaMemcpyHostToDevice, st));
+  return rc;
 }
 
 extern "C" int casa_ransac_vote(casa_handle* h, const casa_ransac_params* p, const float* mask, const float* vertex,
@@ -527,6 +747,12 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   const size_t mask_n = (size_t)p->b * hw * p->oc * 4, vert_n = (size_t)p->b * hw * vfields * p->vn * 2 * 4;
   const size_t out_b = (size_t)p->b * p->oc * p->vn * 2 * 4;
   cudaStream_t st = h->own_stream;
+  struct AsyncOff {  // the parts below are collected one by one
+    casa_handle* h;
+    int saved;
+    explicit AsyncOff(casa_handle* hh) : h(hh), saved(hh->async_mode) { h->async_mode = 0; }
+    ~AsyncOff() { h->async_mode = saved; }
+  } async_off(h);
   // Pinned (page-locked) host buffers: the mask is DMA-copied in up to 4 image ranges on a copy stream while the
   // previous range is being voted on, and the vector field is never copied — k_gather_dirs reads only the masked
   // pixels' rows straight from the mapped host buffer.  About 200 MB instead of 511 MB cross PCIe for a 16-frame
@@ -643,6 +869,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
                off_adj = bump(cur, (size_t)d.J * d.vn * 6 * 4), off_tmp_out = bump(cur, (size_t)d.J * d.vn * 2 * 4);
   rc = ensure(&h->ws_mem, &h->ws_bytes, cur);
   if (rc) return rc;
+  h->clean_ctrl = nullptr;  // the LS layer leaves its own loop state in ctrl / stats
   cudaStream_t st = (cudaStream_t)stream;
   WS ws = make_ws(L, h->ws_mem, true);
   char* base = (char*)h->ws_mem;
@@ -785,8 +1012,31 @@ extern "C" int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t ma
   return CASA_OK;
 }
 
+extern "C" int casa_set_async(casa_handle* h, int enable) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  h->async_mode = enable ? 1 : 0;
+  return CASA_OK;
+}
+
+extern "C" int casa_sync(casa_handle* h) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = collect(h);
+  CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+  CUDA_TRY(cudaMemcpy(h->pinned_sticky, h->sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  const uint32_t st = *h->pinned_sticky;
+  if (st) CUDA_TRY(cudaMemset(h->sticky, 0, sizeof(uint32_t)));
+  if (rc) return rc;
+  if (st & CASA_STATUS_PIX_OVERFLOW)
+    return fail(CASA_ERR_WORKSPACE, "a call since the last casa_sync overflowed its pixel lists (mask not one-hot?); retry with a larger pix_capacity");
+  if (st & CASA_STATUS_IDX_RANGE) return fail(CASA_ERR_INPUT, "a call since the last casa_sync had caller-supplied idxs outside [0, tn)");
+  return CASA_OK;
+}
+
 extern "C" int casa_last_status(casa_handle* h, uint32_t* status) {
   if (!h || !status) return fail(CASA_ERR_INVALID, "NULL argument");
+  const int rc = collect(h);
+  if (rc != CASA_OK && rc != CASA_ERR_WORKSPACE && rc != CASA_ERR_INPUT) return rc;
   *status = h->last_status;
   return CASA_OK;
 }
@@ -799,16 +1049,19 @@ extern "C" int casa_set_timing(casa_handle* h, int enable) {
 
 extern "C" int casa_get_timing(casa_handle* h, double* score_ms, int64_t* score_launches, uint64_t* stats4) {
   if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  collect(h);
   if (score_ms) *score_ms = h->score_ms;
   if (score_launches) *score_launches = h->score_launches;
   if (stats4)
     for (int k = 0; k < 4; ++k) stats4[k] = h->stats[k];
+  if (h->async_mode) reset_totals(h);  // asynchronous callers get the totals since their previous query
   return CASA_OK;
 }
 
 extern "C" int casa_last_launches(casa_handle* h, int64_t* launches) {
   if (!h || !launches) return fail(CASA_ERR_INVALID, "NULL argument");
-  *launches = h->last_launches;
+  collect(h);
+  *launches = h->async_mode ? h->launches_total : h->last_launches;
   return CASA_OK;
 }
 

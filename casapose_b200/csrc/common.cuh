@@ -25,6 +25,8 @@ constexpr int CTRL_WORK = 1;
 constexpr int CTRL_NACTIVE = 2;
 constexpr int CTRL_STATUS = 3;
 constexpr int CTRL_NRTILES = 4;
+constexpr int CTRL_ROUND = 5;   // index of the round the loop body is about to run (device-driven loop, rounds >= 1)
+constexpr int CTRL_DONE = 6;    // k_update blocks finished in this round (the last one decides about the next round)
 constexpr int CTRL_WORDS = 8;
 
 // hypothesis classes written by k_hypgen

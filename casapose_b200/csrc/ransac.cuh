@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
                                                 float* dbg_hyps) {
   const int job = blockIdx.y;
   if (!(ws.job_flags[job] & JOB_ACTIVE)) return;
+  if (rnd < 0) rnd = ws.ctrl[CTRL_ROUND];  // inside the device-driven loop (rounds >= 1)
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e >= d.hn * d.vn) return;
   const int tn = ws.job_tn[job];
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
 // rtile_start[j] = sum over live jobs of ceil(tn/1024)
 __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (rnd < 0) rnd = ws.ctrl[CTRL_ROUND];  // inside the device-driven loop (rounds >= 1)
   __shared__ int swarp[2][32];
   __shared__ int srun[2];
   if (tid < 2) srun[tid] = 0;
@@ -527,61 +529,78 @@ __device__ __forceinline__ bool stop_test(float min_ratio, int hyp_num, float co
 }
 
 // ------------------------------------------------------------------------------------ K3b
-// one block per job, one warp per keypoint
-__global__ void __launch_bounds__(512) k_update(WS ws, Dims d, int rnd, casa_ransac_debug dbg) {
+// one block per job, one warp per keypoint.  The block that finishes last publishes the loop state: the index of the
+// next round and — when the call runs as a CUDA graph — the condition of the graph's WHILE node, so that the
+// reference's data-dependent `while` (:318) never returns to the host.
+__global__ void __launch_bounds__(512) k_update(WS ws, Dims d, int rnd, casa_ransac_debug dbg, unsigned long long cond_handle,
+                                                uint32_t* sticky) {
   const int job = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (rnd < 0) rnd = ws.ctrl[CTRL_ROUND];
   const int flags = ws.job_flags[job];
-  if (!(flags & JOB_ACTIVE)) return;
   __shared__ unsigned long long svbest[16];
-  const int tn = ws.job_tn[job];
-  if (warp < d.vn) {
-    const int* c = ws.counts + ((size_t)job * d.vn + warp) * d.hn;
-    unsigned long long best = 0ull;  // (count << 32) | ~h : max count, then lowest h (:328 argmax takes the first)
-    for (int h = lane; h < d.hn; h += 32) {
-      const unsigned long long key = ((unsigned long long)(unsigned)c[h] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)h);
-      best = key > best ? key : best;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
-      best = y > best ? y : best;
-    }
-    if (lane == 0) svbest[warp] = best;
-  }
-  __syncthreads();
-  if (dbg.counts) {
-    int32_t* dst = dbg.counts + ((size_t)job * d.max_iter + rnd) * d.hn * d.vn;
-    for (int e = tid; e < d.hn * d.vn; e += blockDim.x) {
-      const int h = e / d.vn, v = e - h * d.vn;
-      dst[e] = ws.counts[((size_t)job * d.vn + v) * d.hn + h];
-    }
-  }
-  if (tid < d.vn) ws.n_exact[job * d.vn + tid] = 0;  // for the next round's k_hypgen
-  if (tid == 0) {
-    float min_ratio = 3.0e38f;
-    for (int v = 0; v < d.vn; ++v) {
-      const int cnt = (int)(svbest[v] >> 32);
-      const int widx = (int)(0xFFFFFFFFu - (unsigned)(svbest[v] & 0xFFFFFFFFull));
-      const float ratio = __fdiv_rn((float)cnt, (float)tn);  // :333
-      float best_ratio = ws.win_ratio[job * d.vn + v];
-      if (best_ratio < ratio) {                              // :336-338
-        best_ratio = ratio;
-        ws.win_ratio[job * d.vn + v] = ratio;
-        ws.win_pts[job * d.vn + v] = ws.hyp_true[((size_t)job * d.vn + v) * d.hn + widx];
+  if (flags & JOB_ACTIVE) {  // uniform per block
+    const int tn = ws.job_tn[job];
+    if (warp < d.vn) {
+      const int* c = ws.counts + ((size_t)job * d.vn + warp) * d.hn;
+      unsigned long long best = 0ull;  // (count << 32) | ~h : max count, then lowest h (:328 argmax takes the first)
+      for (int h = lane; h < d.hn; h += 32) {
+        const unsigned long long key = ((unsigned long long)(unsigned)c[h] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)h);
+        best = key > best ? key : best;
       }
-      min_ratio = fminf(min_ratio, best_ratio);              // :342
-      if (dbg.win_idx) dbg.win_idx[((size_t)job * d.max_iter + rnd) * d.vn + v] = widx;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+        best = y > best ? y : best;
+      }
+      if (lane == 0) svbest[warp] = best;
     }
-    const int cur_iter = rnd + 1;                            // :341
-    const int hyp_num = d.hn * cur_iter;                     // :340 (exact in float32 below 2^24)
-    const bool stop = stop_test(min_ratio, hyp_num, d.confidence) || cur_iter >= d.max_iter;  // :344-347
-    ws.job_rounds[job] = cur_iter;
-    if (stop) {
-      ws.job_flags[job] = flags & ~JOB_ACTIVE;
-    } else {
-      atomicAdd(&ws.ctrl[CTRL_NACTIVE], 1);
+    __syncthreads();
+    if (dbg.counts) {
+      int32_t* dst = dbg.counts + ((size_t)job * d.max_iter + rnd) * d.hn * d.vn;
+      for (int e = tid; e < d.hn * d.vn; e += blockDim.x) {
+        const int h = e / d.vn, v = e - h * d.vn;
+        dst[e] = ws.counts[((size_t)job * d.vn + v) * d.hn + h];
+      }
     }
-    atomicAdd(&ws.stats[0], (unsigned long long)tn * d.vn * d.hn);
+    if (tid < d.vn) ws.n_exact[job * d.vn + tid] = 0;  // for the next round's k_hypgen
+    if (tid == 0) {
+      float min_ratio = 3.0e38f;
+      for (int v = 0; v < d.vn; ++v) {
+        const int cnt = (int)(svbest[v] >> 32);
+        const int widx = (int)(0xFFFFFFFFu - (unsigned)(svbest[v] & 0xFFFFFFFFull));
+        const float ratio = __fdiv_rn((float)cnt, (float)tn);  // :333
+        float best_ratio = ws.win_ratio[job * d.vn + v];
+        if (best_ratio < ratio) {                              // :336-338
+          best_ratio = ratio;
+          ws.win_ratio[job * d.vn + v] = ratio;
+          ws.win_pts[job * d.vn + v] = ws.hyp_true[((size_t)job * d.vn + v) * d.hn + widx];
+        }
+        min_ratio = fminf(min_ratio, best_ratio);              // :342
+        if (dbg.win_idx) dbg.win_idx[((size_t)job * d.max_iter + rnd) * d.vn + v] = widx;
+      }
+      const int cur_iter = rnd + 1;                            // :341
+      const int hyp_num = d.hn * cur_iter;                     // :340 (exact in float32 below 2^24)
+      const bool stop = stop_test(min_ratio, hyp_num, d.confidence) || cur_iter >= d.max_iter;  // :344-347
+      ws.job_rounds[job] = cur_iter;
+      if (stop) {
+        ws.job_flags[job] = flags & ~JOB_ACTIVE;
+      } else {
+        atomicAdd(&ws.ctrl[CTRL_NACTIVE], 1);
+      }
+      atomicAdd(&ws.stats[0], (unsigned long long)tn * d.vn * d.hn);
+    }
+  }
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&ws.ctrl[CTRL_DONE], 1) == (int)gridDim.x - 1) {  // every other block has published its state
+      __threadfence();
+      const int nactive = *(volatile int*)&ws.ctrl[CTRL_NACTIVE];
+      ws.ctrl[CTRL_DONE] = 0;
+      ws.ctrl[CTRL_ROUND] = rnd + 1;
+      const unsigned st = (unsigned)ws.ctrl[CTRL_STATUS];  // every status bit is raised before or inside the loop
+      if (st && sticky) atomicOr(sticky, st);              // -> the handle's sticky word (collected by casa_sync)
+      if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, nactive > 0 ? 1u : 0u);
+    }
   }
 }
 

@@ -116,7 +116,7 @@ def ransac_voting_layer_all_masks(
         if debug_hyps:
             dbg["hyps"] = torch.zeros((b, oc, mi, hn, vn, 2), dtype=f32, device=dev)
         dbg_struct = _lib.RansacDebug(**{k: ptr(dbg.get(k)) for k in DEBUG_FIELDS})
-    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device(), current_stream_ptr(dev))
     with torch.cuda.device(dev):
         fn = _lib.lib().casa_ransac_vote_seg if seg_scores else _lib.lib().casa_ransac_vote
         rc = fn(
@@ -143,12 +143,28 @@ def ransac_voting_layer_all_masks_host(mask, vertex, round_hyp_num, inlier_thres
         raise TypeError("mask / vertex must be float32")
     if not (mask_t.is_contiguous() and vertex_t.is_contiguous()):
         raise ValueError("mask / vertex must be C-contiguous")
+    if mask_t.dim() != 4:
+        raise ValueError("mask must be [b,h,w,oc], got %s" % (tuple(mask_t.shape),))
     b, h, w, oc = mask_t.shape
-    vn = vertex_t.shape[3] if vertex_t.dim() == 5 else vertex_t.shape[3] // 2
+    if vertex_t.dim() == 4:
+        if tuple(vertex_t.shape[:3]) != (b, h, w) or vertex_t.shape[3] % 2:
+            raise ValueError("vertex must be [b,h,w,vn*2] matching mask, got %s" % (tuple(vertex_t.shape),))
+        vertex_t = vertex_t.view(b, h, w, vertex_t.shape[3] // 2, 2)
+    vertex_per_class = vertex_t.dim() == 6
+    if vertex_per_class:
+        if tuple(vertex_t.shape[:4]) != (b, h, w, oc) or vertex_t.shape[5] != 2:
+            raise ValueError("per-class vertex must be [b,h,w,oc,vn,2], got %s" % (tuple(vertex_t.shape),))
+    elif vertex_t.dim() != 5 or tuple(vertex_t.shape[:3]) != (b, h, w) or vertex_t.shape[4] != 2:
+        raise ValueError("vertex must be [b,h,w,vn,2] matching mask, got %s" % (tuple(vertex_t.shape),))
+    vn = vertex_t.shape[-2]
     p = _params(b, h, w, oc, vn, round_hyp_num, inlier_thresh, confidence, max_iter, min_num, max_num, seed,
-                image_offset, 0, False)
+                image_offset, 0, False, vertex_per_class)
     if out is None:
         out = torch.empty((b, oc, vn, 2), dtype=torch.float32)
+    else:
+        if not isinstance(out, torch.Tensor) or out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() \
+                or tuple(out.shape) != (b, oc, vn, 2):
+            raise ValueError("out must be a contiguous CPU float32 tensor [b,oc,vn,2] = %s" % ((b, oc, vn, 2),))
     hdl = _lib.handle(device)
     rc = _lib.lib().casa_ransac_vote_host(hdl, C.byref(p), mask_t.data_ptr(), vertex_t.data_ptr(), out.data_ptr())
     _lib.check(rc)
@@ -238,7 +254,7 @@ def pnp_cuda(points_2d, points_3d, camera_matrixes, offsets=None):
     off = put(offsets) if offsets is not None else None
     n, vn = p2.shape[0], p2.shape[1]
     out = torch.empty((n, 3, 4), dtype=torch.float32, device=dev)
-    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device(), current_stream_ptr(dev))
     with torch.cuda.device(dev):
         rc = _lib.lib().casa_pnp(hdl, n, vn, ptr(p2), ptr(p3), ptr(cam), ptr(off), ptr(out), current_stream_ptr(dev))
     _lib.check(rc)
@@ -336,7 +352,7 @@ def pose_errors_cuda(poses, poses_gt, camera_matrixes, model_points, model_count
     if not (gt.shape[0] == cam.shape[0] == dia.shape[0] == val.shape[0] == n and cnt.shape[0] == m):
         raise ValueError("pose_errors_cuda: inconsistent leading dimensions")
     out = torch.empty((n, 6), dtype=torch.float32, device=dev)
-    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device(), current_stream_ptr(dev))
     with torch.cuda.device(dev):
         rc = _lib.lib().casa_pose_errors(hdl, n, m, maxp, ptr(po), ptr(gt), ptr(cam), ptr(pts), ptr(cnt), ptr(om), ptr(dia),
                                          ptr(val), float(allowed_error_2d), ptr(out), current_stream_ptr(dev))

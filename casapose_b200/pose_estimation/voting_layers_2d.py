@@ -95,7 +95,7 @@ class CoordLSVotingWeighted:
         gd = torch.empty((b, h, wd, 2 * vn), dtype=torch.float32, device=dev)
         gw = torch.empty((b, h, wd, vn), dtype=torch.float32, device=dev)
         p = self._params(b, h, wd, nc, vn, False)
-        hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device(), current_stream_ptr(dev))
         with torch.cuda.device(dev):
             rc = _lib.lib().casa_ls_vote_backward(hdl, C.byref(p), ptr(seg), ptr(direct), ptr(w), ptr(grad_out), None, ptr(gd),
                                                   ptr(gw), current_stream_ptr(dev))
@@ -118,7 +118,7 @@ class CoordLSVotingWeighted:
                 "tn": torch.zeros((b, nc - 1), dtype=torch.int32, device=dev),
             }
             dbg_struct = _lib.LsDebug(**{k: ptr(v) for k, v in dbg.items()})
-        hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        hdl = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device(), current_stream_ptr(dev))
         with torch.cuda.device(dev):
             rc = _lib.lib().casa_ls_vote(hdl, C.byref(p), ptr(seg), ptr(direct), ptr(w), ptr(out),
                                          C.byref(dbg_struct) if dbg_struct is not None else None, current_stream_ptr(dev))

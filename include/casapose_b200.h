@@ -221,17 +221,35 @@ int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t maxp, const f
                      const int32_t* obj_model, const float* diameters, const int32_t* valid,
                      float allowed_error_2d, float* out_rows, void* stream);
 
+/*
+ * Synchronous and asynchronous calls.  casa_ransac_vote / casa_ransac_vote_seg enqueue ONE CUDA graph per call on
+ * `stream`: compaction, the first RANSAC round, a device-driven WHILE over the remaining rounds (the reference's
+ * data-dependent tf.while_loop, ransac_voting.py:318-347, never returns to the host), refinement and solve.
+ *   synchronous (default): the call waits for the 32-byte loop state of its own graph — not for refinement and
+ *     solve — and returns CASA_ERR_WORKSPACE / CASA_ERR_INPUT if the device raised a status bit; like the reference's
+ *     eager call, the result tensor itself is complete only after the stream has been synchronised.
+ *   asynchronous (casa_set_async(h, 1)): the call returns as soon as the graph is enqueued, so consecutive calls
+ *     queue back to back on the GPU (the data-parallel serving loop).  casa_sync(h) waits for every call issued on
+ *     the handle (including refinement / solve) and returns the first error any of them raised; at most 256 calls
+ *     may be outstanding before the library collects the oldest ones itself.
+ */
+int casa_set_async(casa_handle* h, int enable);
+int casa_sync(casa_handle* h);
+
 /* Device status word of the last casa_ransac_vote on this handle (CASA_STATUS_* bits). */
 int casa_last_status(casa_handle* h, uint32_t* status);
 /* Number of kernels the last call launched on this handle. */
 int casa_last_launches(casa_handle* h, int64_t* launches);
 
 /*
- * Measurement hooks (bench.py).  With timing enabled every scoring-kernel launch is bracketed by
- * CUDA events on the caller's stream; casa_get_timing returns, for the LAST casa_ransac_vote call,
- * the summed duration of its scoring launches (ms), their number, and the filter statistics
- * stats[0] = units scored (hypothesis x pixel x keypoint tests), stats[1] = units decided by the
- * exact predicate, stats[2] = exact-list hypotheses, stats[3] = stage-2 (hypothesis pair, chunk) events.
+ * Measurement hooks (bench.py).  With timing enabled the scoring-kernel launch of the first round of every call is
+ * bracketed by CUDA events on the caller's stream (event-record nodes of the call's graph; later rounds run inside
+ * the graph's WHILE body, which cannot hold event nodes).  casa_get_timing returns the summed duration of those
+ * launches (ms), their number, and the filter statistics
+ * stats[0] = units scored (hypothesis x pixel x keypoint tests, all rounds), stats[1] = units decided by the
+ * exact predicate, stats[2] = exact-list hypotheses, stats[3] = stage-2 (hypothesis pair, chunk) events
+ * — of the LAST call for a synchronous handle, accumulated over the calls since the previous query for an
+ * asynchronous one (the query collects them, i.e. waits for their loop states).
  */
 int casa_set_timing(casa_handle* h, int enable);
 int casa_get_timing(casa_handle* h, double* score_ms, int64_t* score_launches, uint64_t* stats4);

@@ -169,8 +169,8 @@ namespace {
 struct Layout {
   Dims d;
   size_t off_bits, off_tile_cnt, off_tile_base, off_pix, off_vdir, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
-      off_job_rounds, off_job_selthr, off_win_ratio, off_win_pts, off_hyp_true, off_hyp_filt, off_exact_list,
-      off_n_exact, off_counts, off_item_start, off_rtile_start, off_rtile_job, off_ctrl, off_partial, off_stats, total;
+      off_job_rounds, off_job_done, off_job_selthr, off_win_ratio, off_win_pts, off_hyp_true, off_hyp_filt, off_exact_list,
+      off_n_exact, off_counts, off_item_start, off_rtile_start, off_rtile_job, off_rtile_rec, off_ctrl, off_partial, off_stats, total;
 };
 
 size_t bump(size_t& cur, size_t bytes) {
@@ -202,6 +202,7 @@ int make_layout(const casa_ransac_params* p, Layout& L) {
   if (rtiles > (1ll << 30) || (long long)d.b * ((long long)d.cap / kChunk + d.oc + 1) * d.vn > (1ll << 30))
     return fail(CASA_ERR_INVALID, "too many work items");
   d.max_rtiles = (int)rtiles;
+  d.rtile = kVoteTile;
   d.image_offset = p->image_offset;
   d.seed_lo = (uint32_t)(p->seed & 0xFFFFFFFFull);
   d.seed_hi = (uint32_t)(p->seed >> 32);
@@ -220,6 +221,7 @@ int make_layout(const casa_ransac_params* p, Layout& L) {
   L.off_job_off = bump(cur, J * 4);
   L.off_job_flags = bump(cur, J * 4);
   L.off_job_rounds = bump(cur, J * 4);
+  L.off_job_done = bump(cur, J * 4);
   L.off_job_selthr = bump(cur, J * 4);
   L.off_win_ratio = bump(cur, jv * 4);
   L.off_win_pts = bump(cur, jv * 8);
@@ -231,9 +233,10 @@ int make_layout(const casa_ransac_params* p, Layout& L) {
   L.off_item_start = bump(cur, (J + 1) * 4);
   L.off_rtile_start = bump(cur, (J + 1) * 4);
   L.off_rtile_job = bump(cur, (size_t)d.max_rtiles * 4);
+  L.off_rtile_rec = bump(cur, (size_t)d.max_rtiles * 16);
   L.off_ctrl = bump(cur, CTRL_WORDS * 4);
   L.off_stats = bump(cur, 4 * 8);  // directly behind ctrl: one memset node clears both (run_graph: STEP_CLEAR)
-  L.off_partial = bump(cur, (size_t)d.max_rtiles * d.vn * 5 * 8);
+  L.off_partial = bump(cur, (size_t)(d.max_rtiles > d.J ? d.max_rtiles : d.J) * d.vn * 5 * 8);
   L.total = cur;
   return CASA_OK;
 }
@@ -251,6 +254,7 @@ WS make_ws(const Layout& L, void* base, bool stats) {
   w.job_off = (int*)(b + L.off_job_off);
   w.job_flags = (int*)(b + L.off_job_flags);
   w.job_rounds = (int*)(b + L.off_job_rounds);
+  w.job_done = (int*)(b + L.off_job_done);
   w.job_selthr = (float*)(b + L.off_job_selthr);
   w.win_ratio = (float*)(b + L.off_win_ratio);
   w.win_pts = (float2*)(b + L.off_win_pts);
@@ -262,6 +266,7 @@ WS make_ws(const Layout& L, void* base, bool stats) {
   w.item_start = (int*)(b + L.off_item_start);
   w.rtile_start = (int*)(b + L.off_rtile_start);
   w.rtile_job = (int*)(b + L.off_rtile_job);
+  w.rtile_rec = (int4*)(b + L.off_rtile_rec);
   w.ctrl = (int*)(b + L.off_ctrl);
   w.partial = (double*)(b + L.off_partial);
   w.stats = stats ? (unsigned long long*)(b + L.off_stats) : nullptr;
@@ -657,8 +662,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     steps.push_back(kstep((const void*)k_seg_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d));
   else
     steps.push_back(kstep((const void*)k_mask_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d).arg(vec4));
-  steps.push_back(kstep((const void*)k_scan_tiles, d.J, 128).arg(ws).arg(d));
-  steps.push_back(kstep((const void*)k_job_table, (d.b + 63) / 64, 64).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_job_tables, d.b, 256).arg(ws).arg(d));
   steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
   if ((float)d.hw > p->max_num) steps.push_back(kstep((const void*)k_cap_filter, d.J, 1024).arg(ws).arg(d).arg(selection));
   // round 0's plan only needs the job table: it runs beside the direction gather (side branch, joined by k_hypgen)
@@ -690,8 +694,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   // and solve do not wait for the copy engine
   steps.push_back(special(STEP_READBACK, 1));
   steps.push_back(special(STEP_CLEAR, 2));
-  steps.push_back(kstep((const void*)k_refine, dim3(refine_gx, d.vn), 256).arg(ws).arg(d).arg(fc));
-  steps.push_back(kstep((const void*)k_solve, d.J, 32).arg(ws).arg(d).arg(out_points).arg(dbg));
+  steps.push_back(kstep((const void*)k_refine_solve, dim3(refine_gx, d.vn), kRefineThreads).arg(ws).arg(d).arg(fc).arg(out_points).arg(dbg));
   for (const Step& s2 : steps) base_launches += s2.kind == STEP_KERNEL;
   base_launches -= round_launches;  // the body's kernels are counted per executed round below
   slot->timed = h->timing;
@@ -860,6 +863,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   int rc = make_layout(&rp, L);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
+  L.d.rtile = kRefineTile;
   const Dims& d = L.d;
   const size_t npx = (size_t)d.b * d.hw;
   size_t cur = L.total;
@@ -904,8 +908,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
     if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_ls_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     steps.push_back(kstep((const void*)k_ls_classify, dim3(d.nct, d.b), 256, sm).arg(seg).arg(ws).arg(d).arg(lw).arg(ld));
   }
-  steps.push_back(kstep((const void*)k_scan_tiles, d.J, 128).arg(ws).arg(d));
-  steps.push_back(kstep((const void*)k_job_table, (d.b + 63) / 64, 64).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_job_tables, d.b, 256).arg(ws).arg(d));
   steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
   steps.push_back(kstep((const void*)k_plan, 1, 256).arg(ws).arg(d).arg((int)0));
   const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;

@@ -11,7 +11,8 @@ constexpr int kCountTile = 1024;   // pixels per block in the mask / scatter ker
 constexpr int kScoreWarps = 8;     // warps per scoring block
 constexpr int kScoreThreads = kScoreWarps * 32;
 constexpr int kChunk = 128;        // pixels per scoring work item (one warp)
-constexpr int kRefineTile = 1024;  // pixels per refinement block
+constexpr int kRefineTile = 1024;  // pixels per reduction tile of the LS layer (256 threads x 4)
+constexpr int kVoteTile = 2048;    // pixels per refinement tile of the voting path (256 threads x 8)
 
 // job flag bits
 constexpr int JOB_GATED = 1;     // foreground_num < min_num  -> zeros   (ransac_voting.py:290)
@@ -56,6 +57,7 @@ struct WS {
   int* job_off;        // [J]
   int* job_flags;      // [J]
   int* job_rounds;     // [J]
+  int* job_done;       // [J]            refinement blocks of the job that have finished (the last one solves)
   float* job_selthr;   // [J]            max_num / foreground_num          (:298)
   float* win_ratio;    // [J][vn]
   float2* win_pts;     // [J][vn]
@@ -67,14 +69,17 @@ struct WS {
   int* item_start;     // [J+1]          exclusive prefix of scoring work items (chunks x vn) over active jobs
   int* rtile_start;    // [J+1]          exclusive prefix of refinement tiles over live jobs
   int* rtile_job;      // [max_rtiles]   job of every refinement tile (written by k_plan in round 0)
+  int4* rtile_rec;     // [max_rtiles]   (job, tile, tn, list offset) of every refinement tile (k_plan, round 0)
   int* ctrl;           // [CTRL_WORDS]
-  double* partial;     // [max_rtiles][vn][5]  per-tile sums nx*nx, nx*ny, ny*ny, nx*b, ny*b
+  double* partial;     // [max(max_rtiles, J)][vn][5]  sums nx*nx, nx*ny, ny*ny, nx*b, ny*b: per (job, keypoint) in the
+                       //                voting path, per tile in the LS layer
   unsigned long long* stats;  // [4]
 };
 
 struct Dims {
   int b, h, w, oc, vn, hn, max_iter;
   int hw, J, nct, cap, max_rtiles;
+  int rtile;  // pixels per refinement tile: kVoteTile (voting) or kRefineTile (LS layer)
   int image_offset;
   uint32_t seed_lo, seed_hi;
   float min_num, max_num, confidence;

@@ -5,8 +5,8 @@
 // pairs of the batch at once:
 //   k_mask_bits   reads the float mask ONCE (the only pass over [b,h,w,oc]), writes one
 //                 class-membership word per pixel and per-tile class counts (warp ballots);
-//   k_scan_tiles  exclusive prefix over the tiles of each (image, class);
-//   k_job_table   class offsets, foreground_num gate (:290), down-sampling threshold (:298);
+//   k_job_tables  exclusive prefix over the tiles of each (image, class); class offsets, foreground_num gate (:290),
+//                 down-sampling threshold (:298);
 //   k_scatter     raster-order scatter of packed pixel coordinates (y<<16 | x) — the order is
 //                 semantically required because hypothesis indices address this list (:216);
 //   k_cap_filter  in-place ordered filter  selection < max_num / foreground_num  (:295-301).
@@ -135,41 +135,42 @@ __global__ void __launch_bounds__(256) k_seg_bits(const float* __restrict__ seg,
   if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
 }
 
-// one block (128 threads) per job: exclusive prefix of the job's tile counts, foreground_num (:287)
-__global__ void __launch_bounds__(128) k_scan_tiles(WS ws, Dims d) {
-  const int job = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int swarp[4];
-  __shared__ int srun;
-  const int* cnt = ws.tile_cnt + (size_t)job * d.nct;
-  int* base = ws.tile_base + (size_t)job * d.nct;
-  if (tid == 0) srun = 0;
-  __syncthreads();
-  for (int s = 0; s < d.nct; s += 128) {
-    const int i = s + tid;
-    const int v = i < d.nct ? cnt[i] : 0;
-    int x = v;
+// One block (256 threads) per image.  Warps stride over the image's classes: exclusive prefix of the class's tile
+// counts (tile_base) and foreground_num (:287); then one thread lays out the image's pixel list: class offsets, the
+// foreground_num gate (:290), the down-sampling threshold (:298).
+__global__ void __launch_bounds__(256) k_job_tables(WS ws, Dims d) {
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = warp; c < d.oc; c += 8) {
+    const int job = img * d.oc + c;
+    const int* cnt = ws.tile_cnt + (size_t)job * d.nct;
+    int* base = ws.tile_base + (size_t)job * d.nct;
+    int run = 0;
+    for (int s = 0; s < d.nct; s += 32 * 16) {  // every lane takes 16 consecutive tiles: all loads in flight at once
+      int v[16];
+      const int i0 = s + lane * 16;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      for (int k = 0; k < 16; ++k) v[k] = i0 + k < d.nct ? cnt[i0 + k] : 0;
+      int tot = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tot += v[k];
+      int x = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      int acc = run + x - tot;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (i0 + k < d.nct) base[i0 + k] = acc;
+        acc += v[k];
+      }
+      run += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (lane == 31) swarp[warp] = x;
-    __syncthreads();
-    int woff = 0;
-    for (int k = 0; k < warp; ++k) woff += swarp[k];
-    const int run = srun;
-    if (i < d.nct) base[i] = run + woff + x - v;
-    __syncthreads();
-    if (tid == 127) srun = run + woff + x;
-    __syncthreads();
+    if (lane == 0) ws.job_tn0[job] = run;
   }
-  if (tid == 0) ws.job_tn0[job] = srun;
-}
-
-// one thread per image: class offsets inside the image's pixel list, gate (:290), cap threshold (:298)
-__global__ void __launch_bounds__(64) k_job_table(WS ws, Dims d) {
-  const int img = blockIdx.x * 64 + threadIdx.x;
-  if (img >= d.b) return;
+  __syncthreads();
+  if (tid != 0) return;
   int off = 0;
   for (int c = 0; c < d.oc; ++c) {
     const int job = img * d.oc + c;
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(64) k_job_table(WS ws, Dims d) {
     ws.job_off[job] = off;
     ws.job_flags[job] = flags;
     ws.job_rounds[job] = 0;
+    ws.job_done[job] = 0;
     ws.job_selthr[job] = thr;
     if (!(flags & JOB_OVERFLOW)) off += tn0;
   }

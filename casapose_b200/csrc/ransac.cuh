@@ -7,8 +7,8 @@
 //                items / refinement tiles over the jobs
 //   k_score      THE HOT KERNEL: hypotheses x pixels inlier test (:230-249) and vote counts (:327)
 //   k_update     arg-max per keypoint (:328-333), best-so-far update (:336-338), stop test (:340-347)
-//   k_refine     re-vote of the winners and per-tile normal-equation sums (:349-362)
-//   k_solve      ordered sum of the tiles, invertibility test and 2x2 solve (:254-272, :364-368)
+//   k_refine_solve  re-vote of the winners, normal-equation sums (:349-362); the job's last block applies the
+//                invertibility test and the 2x2 solve (:254-272, :364-368)
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
         }
       }
       if (flags & JOB_ACTIVE) ci = ((tn + kChunk - 1) / kChunk) * d.vn;
-      if (!(flags & JOB_GATED) && tn > 0) cr = (tn + kRefineTile - 1) / kRefineTile;
+      if (!(flags & JOB_GATED) && tn > 0) cr = (tn + d.rtile - 1) / d.rtile;
     }
     int xi = ci, xr = cr;
 #pragma unroll
@@ -133,7 +133,11 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
       if (rnd == 0) {
         const int r0 = rr + wr + xr - cr;
         ws.rtile_start[job] = r0;
-        for (int k = 0; k < cr; ++k) ws.rtile_job[r0 + k] = job;
+        const int4 rec = make_int4(job, 0, ws.job_tn[job], ws.job_off[job]);
+        for (int k = 0; k < cr; ++k) {
+          ws.rtile_job[r0 + k] = job;
+          ws.rtile_rec[r0 + k] = make_int4(rec.x, k, rec.z, rec.w);
+        }
       }
     }
     __syncthreads();
@@ -563,33 +567,38 @@ __global__ void __launch_bounds__(512) k_update(WS ws, Dims d, int rnd, casa_ran
       }
     }
     if (tid < d.vn) ws.n_exact[job * d.vn + tid] = 0;  // for the next round's k_hypgen
-    if (tid == 0) {
-      float min_ratio = 3.0e38f;
-      for (int v = 0; v < d.vn; ++v) {
+    if (warp == 0) {  // lane v: best-so-far update of keypoint v (:333-338), then the stop test on the minimum (:342-347)
+      float best_ratio = 3.0e38f;
+      if (lane < d.vn) {
+        const int v = lane;
         const int cnt = (int)(svbest[v] >> 32);
         const int widx = (int)(0xFFFFFFFFu - (unsigned)(svbest[v] & 0xFFFFFFFFull));
         const float ratio = __fdiv_rn((float)cnt, (float)tn);  // :333
-        float best_ratio = ws.win_ratio[job * d.vn + v];
+        best_ratio = ws.win_ratio[job * d.vn + v];
         if (best_ratio < ratio) {                              // :336-338
           best_ratio = ratio;
           ws.win_ratio[job * d.vn + v] = ratio;
           ws.win_pts[job * d.vn + v] = ws.hyp_true[((size_t)job * d.vn + v) * d.hn + widx];
         }
-        min_ratio = fminf(min_ratio, best_ratio);              // :342
         if (dbg.win_idx) dbg.win_idx[((size_t)job * d.max_iter + rnd) * d.vn + v] = widx;
       }
-      const int cur_iter = rnd + 1;                            // :341
-      const int hyp_num = d.hn * cur_iter;                     // :340 (exact in float32 below 2^24)
-      const bool stop = stop_test(min_ratio, hyp_num, d.confidence) || cur_iter >= d.max_iter;  // :344-347
-      ws.job_rounds[job] = cur_iter;
-      if (stop) {
-        ws.job_flags[job] = flags & ~JOB_ACTIVE;
-      } else {
-        atomicAdd(&ws.ctrl[CTRL_NACTIVE], 1);
+      float min_ratio = best_ratio;                            // :342 (ratios are non-negative: they order like their bits)
+      min_ratio = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(min_ratio)));
+      if (lane == 0) {
+        const int cur_iter = rnd + 1;                            // :341
+        const int hyp_num = d.hn * cur_iter;                     // :340 (exact in float32 below 2^24)
+        const bool stop = stop_test(min_ratio, hyp_num, d.confidence) || cur_iter >= d.max_iter;  // :344-347
+        ws.job_rounds[job] = cur_iter;
+        if (stop) {
+          ws.job_flags[job] = flags & ~JOB_ACTIVE;
+        } else {
+          atomicAdd(&ws.ctrl[CTRL_NACTIVE], 1);
+        }
+        atomicAdd(&ws.stats[0], (unsigned long long)tn * d.vn * d.hn);
       }
-      atomicAdd(&ws.stats[0], (unsigned long long)tn * d.vn * d.hn);
     }
   }
+  __syncthreads();
   if (tid == 0) {
     __threadfence();
     if (atomicAdd(&ws.ctrl[CTRL_DONE], 1) == (int)gridDim.x - 1) {  // every other block has published its state
@@ -605,70 +614,6 @@ __global__ void __launch_bounds__(512) k_update(WS ws, Dims d, int rnd, casa_ran
 }
 
 // ------------------------------------------------------------------------------------ K4
-// grid (<= n_rtiles, vn), blocks stride over the (1024-pixel tile of a job, keypoint) pairs; 4 pixels per thread.
-// Re-votes the winner (:353) and accumulates the normal equations (:356-362): float32 products exactly
-// as the reference forms them (normal * inlier flag, so a non-finite direction poisons the sums as it
-// does there), float64 accumulation, fixed reduction order.
-__global__ void __launch_bounds__(256) k_refine(WS ws, Dims d, FilterConsts fc) {
-  const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_rtiles = ws.rtile_start[d.J];
-  __shared__ double sred[8][5];
-  for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
-  const int job = ws.rtile_job[rt], tile = rt - ws.rtile_start[job];
-  const int tn = ws.job_tn[job];
-  const int img = job / d.oc;
-  const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
-  const float2* vd = job_dirs(ws, d, img, job, tn, v);
-  const float2 wp = ws.win_pts[job * d.vn + v];
-  double s[5] = {0, 0, 0, 0, 0};
-  // phase 1: all loads of the thread's 4 pixels in flight together; phase 2: arithmetic
-  uint32_t lp_[kRefineTile / 256];
-  float2 ld_[kRefineTile / 256];
-#pragma unroll
-  for (int k = 0; k < kRefineTile / 256; ++k) {
-    const int t = tile * kRefineTile + k * 256 + tid;
-    lp_[k] = t < tn ? pix[t] : 0u;
-    ld_[k] = t < tn ? load_dir(vd, t) : make_float2(0.f, 0.f);
-  }
-#pragma unroll
-  for (int k = 0; k < kRefineTile / 256; ++k) {
-    const int t = tile * kRefineTile + k * 256 + tid;
-    if (t < tn) {
-      const uint32_t pk = lp_[k];
-      const int x = pk & 0xFFFFu, y = pk >> 16;
-      const float2 dv = ld_[k];
-      const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
-      const bool in = exact_inlier(wp.x, wp.y, cx, cy, dv.x, dv.y, exact_norm(dv.x, dv.y), fc.thr);  // :353
-      const bool finite = fabsf(dv.x) <= 3.0e38f && fabsf(dv.y) <= 3.0e38f;
-      if (in || !finite) {  // finite outliers contribute exact zeros
-        const float fl = in ? 1.0f : 0.0f;
-        const float nx = __fmul_rn(__fmul_rn(dv.y, -1.0f), fl);  // normal = (-dy, dx) * inlier      :349, :356
-        const float ny = __fmul_rn(dv.x, fl);
-        const float bb = __fadd_rn(__fmul_rn(nx, cx), __fmul_rn(ny, cy));  // :359
-        s[0] += (double)__fmul_rn(nx, nx);  // :361
-        s[1] += (double)__fmul_rn(nx, ny);
-        s[2] += (double)__fmul_rn(ny, ny);
-        s[3] += (double)__fmul_rn(nx, bb);  // :362
-        s[4] += (double)__fmul_rn(ny, bb);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
-    if (lane == 0) sred[warp][k] = s[k];
-  }
-  __syncthreads();
-  if (tid < 5) {
-    double t = 0;
-    for (int k = 0; k < 8; ++k) t += sred[k][tid];
-    ws.partial[((size_t)rt * d.vn + v) * 5 + tid] = t;
-  }
-  __syncthreads();
-  }
-}
-
 // condition number of [[a,b],[b,c]], closed form in float64 (oracle: cond_2x2_sym_f64)
 __device__ __forceinline__ bool invertible_2x2(float af, float bf, float cf) {
   const double a = af, b = bf, c = cf;
@@ -687,54 +632,162 @@ __device__ __forceinline__ bool invertible_2x2(float af, float bf, float cf) {
   return isfinite(cnd) && cnd < 1000000.0;  // :270-272, eps_inv = float32(1/1e-6)
 }
 
-// one warp per job, lane v handles keypoint v
-__global__ void __launch_bounds__(32) k_solve(WS ws, Dims d, float* __restrict__ out, casa_ransac_debug dbg) {
-  const int job = blockIdx.x, v = threadIdx.x;
+constexpr int kRefineThreads = 256;
+
+// lane u of one warp: sums of keypoint u -> invertibility (:364, all-or-nothing), solve (:367), outputs of the job
+__device__ __forceinline__ void solve_job(const WS& ws, const Dims& d, int job, bool dead, const float (&q)[5], bool inv,
+                                          float* __restrict__ out, const casa_ransac_debug& dbg) {
+  const int u = threadIdx.x & 31;
   const int flags = ws.job_flags[job];
   const int tn = ws.job_tn[job];
-  const bool dead = (flags & JOB_GATED) || tn <= 0;
-  float s[5] = {0, 0, 0, 0, 0};
-  bool inv = true;
-  if (!dead && v < d.vn) {
-    const int r0 = ws.rtile_start[job], r1 = ws.rtile_start[job + 1];
-    double acc[5] = {0, 0, 0, 0, 0};
-    for (int rt = r0; rt < r1; ++rt)  // tiles in order: bit-reproducible sums
-#pragma unroll
-      for (int k = 0; k < 5; ++k) acc[k] += ws.partial[((size_t)rt * d.vn + v) * 5 + k];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) s[k] = (float)acc[k];  // ATA / ATb are float32 tensors in the reference
-    inv = invertible_2x2(s[0], s[1], s[2]);
-  }
   const bool all_inv = !dead && __all_sync(0xffffffffu, inv);  // :364 — one singular keypoint un-refines all
-  if (v < d.vn) {
+  if (u < d.vn) {
     float2 r = make_float2(0.f, 0.f);  // :291-292
     if (!dead) {
-      r = ws.win_pts[job * d.vn + v];  // :364-365
+      r = ws.win_pts[job * d.vn + u];  // :364-365
       if (all_inv) {                   // :367  inv(ATA) @ ATb, closed form in float64 on the float32 sums
-        const double a = s[0], b = s[1], c = s[2], g0 = s[3], g1 = s[4];
-        const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, b));
-        r.x = (float)__ddiv_rn(__dsub_rn(__dmul_rn(c, g0), __dmul_rn(b, g1)), det);
-        r.y = (float)__ddiv_rn(__dsub_rn(__dmul_rn(a, g1), __dmul_rn(b, g0)), det);
+        const double a = q[0], bq = q[1], c = q[2], g0 = q[3], g1 = q[4];
+        const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(bq, bq));
+        r.x = (float)__ddiv_rn(__dsub_rn(__dmul_rn(c, g0), __dmul_rn(bq, g1)), det);
+        r.y = (float)__ddiv_rn(__dsub_rn(__dmul_rn(a, g1), __dmul_rn(bq, g0)), det);
       }
     }
-    reinterpret_cast<float2*>(out)[(size_t)job * d.vn + v] = r;
+    reinterpret_cast<float2*>(out)[(size_t)job * d.vn + u] = r;
     if (dbg.ata) {
-      float* q = dbg.ata + ((size_t)job * d.vn + v) * 3;
-      q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+      float* o = dbg.ata + ((size_t)job * d.vn + u) * 3;
+      o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
     }
     if (dbg.atb) {
-      float* q = dbg.atb + ((size_t)job * d.vn + v) * 2;
-      q[0] = s[3]; q[1] = s[4];
+      float* o = dbg.atb + ((size_t)job * d.vn + u) * 2;
+      o[0] = q[3]; o[1] = q[4];
     }
-    if (dbg.win_pts) reinterpret_cast<float2*>(dbg.win_pts)[(size_t)job * d.vn + v] = dead ? make_float2(0.f, 0.f) : ws.win_pts[job * d.vn + v];
-    if (dbg.win_ratio) dbg.win_ratio[(size_t)job * d.vn + v] = dead ? 0.f : ws.win_ratio[job * d.vn + v];
+    if (dbg.win_pts) reinterpret_cast<float2*>(dbg.win_pts)[(size_t)job * d.vn + u] = dead ? make_float2(0.f, 0.f) : ws.win_pts[job * d.vn + u];
+    if (dbg.win_ratio) dbg.win_ratio[(size_t)job * d.vn + u] = dead ? 0.f : ws.win_ratio[job * d.vn + u];
   }
-  if (v == 0) {
+  if (u == 0) {
     if (dbg.refined) dbg.refined[job] = all_inv ? 1 : 0;
     if (dbg.tn0) dbg.tn0[job] = ws.job_tn0[job];
     if (dbg.tn) dbg.tn[job] = (flags & JOB_GATED) ? 0 : tn;
     if (dbg.rounds) dbg.rounds[job] = dead ? 0 : ws.job_rounds[job];
     if (dbg.pix_off) dbg.pix_off[job] = ws.job_off[job];
+  }
+}
+
+// K4 — refinement and solve.  grid (<= n_rtiles, vn): blocks stride over the (2048-pixel tile of a job, keypoint)
+// pairs, 8 pixels per thread (all 16 loads of a thread in flight together).  A block re-votes the winner over its tile (:353) and accumulates the normal equations
+// (:356-362): float32 products exactly as the reference forms them (normal * inlier flag, so a non-finite direction
+// poisons the sums as it does there), float64 accumulation, fixed reduction order.  The block that finishes a job's
+// last (tile, keypoint) pair sums the tiles in order (bit-reproducible), applies the all-or-nothing invertibility
+// rule (:364-365) and solves all keypoints of the job (:254-272, :367) — no second kernel.  Jobs without tiles
+// (gated, empty) get their zeros from the blocks' first warps.
+__global__ void __launch_bounds__(kRefineThreads) k_refine_solve(WS ws, Dims d, FilterConsts fc, float* __restrict__ out,
+                                                                 casa_ransac_debug dbg) {
+  const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_rtiles = ws.rtile_start[d.J];
+  __shared__ double sred[kRefineThreads / 32][5];
+  __shared__ int s_last;
+  if (warp == 0 && v == 0) {  // dead jobs: zeros (:291-292) and the debug rows
+    for (int job = blockIdx.x; job < d.J; job += gridDim.x) {
+      const int tn = ws.job_tn[job];
+      if ((ws.job_flags[job] & JOB_GATED) || tn <= 0) {
+        const float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        solve_job(ws, d, job, true, q, true, out, dbg);
+      }
+    }
+  }
+  for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
+    const int4 rec = __ldg(&ws.rtile_rec[rt]);  // (job, tile, tn, list offset): one load instead of a chain of three
+    const int job = rec.x, tile = rec.y, tn = rec.z;
+    const int img = job / d.oc;
+    const uint32_t* pix = ws.pix + (size_t)img * d.cap + rec.w;
+    const float2* vd = ws.vdir + ((size_t)img * d.cap + rec.w) * d.vn + (size_t)v * tn;
+    const float2 wp = ws.win_pts[job * d.vn + v];
+    // The re-vote uses the filtered predicate in its direct form (hd = fl(h - c) is the reference's own difference,
+    // no chunk origin): t = |d^ x hd| - k d^.hd decides unless |t| < c1 |hd|_1 (c1 >= w + e1 bounds the band and the
+    // evaluation error relative to |hd| <= |hd|_1, predicate.cuh; scripts/check_band.py (6)); units inside the band,
+    // directions the filter cannot take and winners outside the filter's hypothesis class get the exact sequence.
+    // The inlier SET is therefore the reference's, at a quarter of the instructions (IEEE sqrt and divide otherwise).
+    const bool fast = fc.fast_ok != 0 && classify_hypothesis(wp.x, wp.y, true) == 0;
+    double s[5] = {0, 0, 0, 0, 0};
+    // phase 1: all loads of the thread's 4 pixels in flight together; phase 2: arithmetic
+    uint32_t lp_[kVoteTile / kRefineThreads];
+    float2 ld_[kVoteTile / kRefineThreads];
+#pragma unroll
+    for (int k = 0; k < kVoteTile / kRefineThreads; ++k) {
+      const int t = tile * kVoteTile + k * kRefineThreads + tid;
+      lp_[k] = t < tn ? pix[t] : 0u;
+      ld_[k] = t < tn ? load_dir(vd, t) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kVoteTile / kRefineThreads; ++k) {
+      const int t = tile * kVoteTile + k * kRefineThreads + tid;
+      if (t < tn) {
+        const uint32_t pk = lp_[k];
+        const int x = pk & 0xFFFFu, y = pk >> 16;
+        const float2 dv = ld_[k];
+        const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
+        bool in = false, decided = false;
+        PixCoef pc;
+        if (fast && make_coef(dv.x, dv.y, fc.k_mid, pc)) {
+          const float hdx = wp.x - cx, hdy = wp.y - cy;  // the reference's rounded difference (:236)
+          const float pv = fmaf(pc.D, hdy, -(pc.E * hdx));
+          const float tv = fabsf(pv) - fmaf(pc.G, hdx, pc.H * hdy);
+          decided = !(fabsf(tv) < fc.c1 * (fabsf(hdx) + fabsf(hdy)));
+          in = (__float_as_uint(tv) >> 31) != 0u;
+        }
+        if (!decided) in = exact_inlier(wp.x, wp.y, cx, cy, dv.x, dv.y, exact_norm(dv.x, dv.y), fc.thr);  // :353
+        const bool finite = fabsf(dv.x) <= 3.0e38f && fabsf(dv.y) <= 3.0e38f;
+        if (in || !finite) {  // finite outliers contribute exact zeros
+          const float fl = in ? 1.0f : 0.0f;
+          const float nx = __fmul_rn(__fmul_rn(dv.y, -1.0f), fl);  // normal = (-dy, dx) * inlier      :349, :356
+          const float ny = __fmul_rn(dv.x, fl);
+          const float bb = __fadd_rn(__fmul_rn(nx, cx), __fmul_rn(ny, cy));  // :359
+          s[0] += (double)__fmul_rn(nx, nx);  // :361
+          s[1] += (double)__fmul_rn(nx, ny);
+          s[2] += (double)__fmul_rn(ny, ny);
+          s[3] += (double)__fmul_rn(nx, bb);  // :362
+          s[4] += (double)__fmul_rn(ny, bb);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+      if (lane == 0) sred[warp][k] = s[k];
+    }
+    __syncthreads();
+    if (tid < 5) {
+      double t = 0;
+      for (int k = 0; k < kRefineThreads / 32; ++k) t += sred[k][tid];
+      ws.partial[((size_t)rt * d.vn + v) * 5 + tid] = t;
+    }
+    __syncthreads();
+    // the block that finishes the job's last (tile, keypoint) pair solves the job
+    const int r0 = rt - tile, r1 = r0 + (tn + kVoteTile - 1) / kVoteTile;
+    if (tid == 0) {
+      __threadfence();
+      s_last = atomicAdd(&ws.job_done[job], 1) == (r1 - r0) * d.vn - 1;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+      __threadfence();
+      float q[5] = {0, 0, 0, 0, 0};
+      bool inv = true;
+      if (lane < d.vn) {
+        double acc[5] = {0, 0, 0, 0, 0};
+        for (int r = r0; r < r1; ++r) {  // tiles in order: bit-reproducible sums
+          const volatile double* ps = ws.partial + ((size_t)r * d.vn + lane) * 5;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) acc[k] += ps[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) q[k] = (float)acc[k];  // ATA / ATb are float32 tensors in the reference
+        inv = invertible_2x2(q[0], q[1], q[2]);
+      }
+      solve_job(ws, d, job, false, q, inv, out, dbg);
+    }
+    __syncthreads();
   }
 }
 

@@ -15,6 +15,8 @@ and asserts the three statements the derivation in predicate.cuh rests on:
   (4) |t_eval - t*| <= e1 (|h'| + R) + (d_fil / cos(theta0)) |hd|        (evaluation error + coefficient rounding)
   (5) sign(t_eval) == verdict   whenever |t_eval| >= c1 (|h'| + R)       (what the main loop relies on)
       sign(t_eval) == verdict   whenever |t_eval| >= kappa2 |p| + e1f (|h'| + R)   (what stage 2 relies on)
+  (6) the direct form of the refinement's re-vote (k_refine_solve: hd = fl(h - c), no chunk origin):
+      sign(t_direct) == verdict whenever |t_direct| >= c1 (|hdx| + |hdy|)
 
 with R = this pixel's own offset from the chunk origin (the smallest radius a chunk containing it can have: the
 tightest bound the kernel can ever apply).  It prints the observed maxima next to the budgets, i.e. the margins.
@@ -121,6 +123,13 @@ def run(thr32, spread, n, rng):
     sure_unit = ~(np.abs(t) < fma32(np.full(n, k["kappa2"], F), np.abs(p), (k["e1"] * nrm).astype(F)))
     bad = (keep & sure_chunk & (sign_in != verdict)).sum() + (keep & sure_unit & (sign_in != verdict)).sum()
     assert bad == 0, "(5) %d units decided wrongly outside the band" % bad
+    # ---- (6) the direct form of k_refine_solve: hd = fl(h - c) itself, no chunk origin, band c1 |hd|_1
+    pd = fma32(D, hdy, -(E * hdx).astype(F))
+    td = (np.abs(pd) - fma32(G, hdx, (H * hdy).astype(F))).astype(F)
+    sure_d = ~(np.abs(td) < (k["c1"] * (np.abs(hdx) + np.abs(hdy)).astype(F)).astype(F))
+    sign_d = np.signbit(td) & ~np.isnan(td)
+    bad_d = (keep & sure_d & (sign_d != verdict)).sum()
+    assert bad_d == 0, "(6) %d units decided wrongly by the direct form" % bad_d
     return dict(n=int(keep.sum()), ref_err_u=float(err1.max() / U), dC_u=k["dC"] / U,
                 eval_err=float((err4 / bud4).max()), uncertain=float((keep & ~sure_unit).mean()),
                 flips=int((keep & (sign_in != verdict)).sum()))
@@ -135,7 +144,7 @@ def main():
             r = run(F(thr), spread, n, rng)
             print("%-8g %-9g %-8d %6.2f (%5.2f)          %6.3f                  %8.5f    %d"
                   % (thr, spread, r["n"], r["ref_err_u"], r["dC_u"], r["eval_err"], r["uncertain"], r["flips"]))
-    print("check_band ok: (1), (4), (5) hold on every sample")
+    print("check_band ok: (1), (4), (5), (6) hold on every sample")
 
 
 if __name__ == "__main__":

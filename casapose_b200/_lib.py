@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("CASA_LIB_PATH") or os.path.join(CSRC, "libcasapose_b200.so")  # override: A/B runs only
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-ldl",
 ]
 
 STATUS_BITS = {
@@ -80,6 +80,13 @@ EXPORTS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "casa_set_async": (C.c_int, [C.c_void_p, C.c_int]),
     "casa_sync": (C.c_int, [C.c_void_p]),
+    "casa_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "casa_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "casa_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "casa_comm_destroy": (C.c_int, [C.c_void_p]),
+    "casa_allgather_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "casa_allgather_points_overlapped": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "casa_gather_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "casa_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "casa_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "casa_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -1,5 +1,6 @@
 // C ABI of casapose_b200 (include/casapose_b200.h): host-side orchestration of the kernels.
 // Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -69,6 +70,11 @@ struct casa_handle {
   unsigned long long* pinned_stats = nullptr;  // 4 words, page-locked
   int score_occ = 0;
   int use_graph = 1;
+  // keypoint all-gather (NCCL, resolved with dlopen: the library itself does not link against it)
+  void* comm = nullptr;           // ncclComm_t
+  int comm_owned = 0, comm_rank = 0, comm_world = 1;
+  cudaStream_t gather_stream = nullptr;
+  cudaEvent_t gather_after[4] = {nullptr, nullptr, nullptr, nullptr}, gather_done[4] = {nullptr, nullptr, nullptr, nullptr};
   CallSlot slots[kCallSlots];
   char* slot_mem = nullptr;       // page-locked backing store of the slots' read-back buffers
   int64_t slot_head = 0, slot_tail = 0;  // calls issued / calls collected (pending = head - tail)
@@ -88,6 +94,53 @@ struct casa_graph {
   cudaGraphConditionalHandle cond = 0;  // condition of the graph's WHILE node (0: the list has no loop)
   cudaGraphNode_t ev0_node = nullptr, ev1_node = nullptr, evr_node = nullptr, ctrl_node = nullptr, stats_node = nullptr;
 };
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+// Only the final [b, oc, vn, 2] keypoints of every rank are exchanged.  NCCL is resolved at run time
+// so that the library loads on machines without it; in a process that already carries an NCCL (PyTorch's,
+// TensorFlow's) dlopen returns that copy.
+namespace {
+struct NcclId128 {  // ncclUniqueId: 128 opaque bytes, passed by value
+  char b[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+  if (g_nccl.lib) return CASA_OK;
+  const char* names[] = {getenv("CASA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names)
+    if (n && !lib) lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(CASA_ERR_INVALID, "NCCL not found (dlopen libnccl.so.2: %s); set CASA_NCCL_LIB", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(lib, "ncclAllGather");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather)
+    return fail(CASA_ERR_INVALID, "NCCL library lacks a required symbol");
+  g_nccl.lib = lib;
+  return CASA_OK;
+}
+
+#define NCCL_TRY(expr)                                                                                     \
+  do {                                                                                                     \
+    const int r__ = (expr);                                                                                \
+    if (r__ != 0)                                                                                          \
+      return fail(CASA_ERR_CUDA, "%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "NCCL error"); \
+  } while (0)
+}  // namespace
+
+struct casa_handle;
+static void comm_release(casa_handle* h);
 
 extern "C" int casa_version(void) { return CASA_VERSION; }
 extern "C" const char* casa_last_error(void) { return g_err; }
@@ -137,6 +190,12 @@ extern "C" int casa_destroy(casa_handle* h) {
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
     delete g;
+  }
+  comm_release(h);
+  if (h->gather_stream) cudaStreamDestroy(h->gather_stream);
+  for (int i = 0; i < 4; ++i) {
+    if (h->gather_after[i]) cudaEventDestroy(h->gather_after[i]);
+    if (h->gather_done[i]) cudaEventDestroy(h->gather_done[i]);
   }
   if (h->ws_mem) cudaFree(h->ws_mem);
   if (h->io_mem) cudaFree(h->io_mem);
@@ -1068,6 +1127,102 @@ extern "C" int casa_last_launches(casa_handle* h, int64_t* launches) {
   return CASA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ keypoint gather
+
+static void comm_release(casa_handle* h) {
+  if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  h->comm_owned = 0;
+}
+
+extern "C" int casa_nccl_unique_id(void* id128) {
+  if (!id128) return fail(CASA_ERR_INVALID, "NULL argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  NCCL_TRY(g_nccl.GetUniqueId(id128));
+  return CASA_OK;
+}
+
+extern "C" int casa_comm_init(casa_handle* h, const void* id128, int rank, int world) {
+  if (!h || !id128) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(CASA_ERR_INVALID, "rank %d of %d", rank, world);
+  int rc = nccl_load();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  comm_release(h);
+  NcclId128 id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_TRY(g_nccl.CommInitRank(&h->comm, world, id, rank));
+  h->comm_owned = 1;
+  h->comm_rank = rank;
+  h->comm_world = world;
+  return CASA_OK;
+}
+
+extern "C" int casa_comm_attach(casa_handle* h, void* nccl_comm, int rank, int world) {
+  if (!h || !nccl_comm) return fail(CASA_ERR_INVALID, "NULL argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  comm_release(h);
+  h->comm = nccl_comm;
+  h->comm_rank = rank;
+  h->comm_world = world;
+  return CASA_OK;
+}
+
+extern "C" int casa_comm_destroy(casa_handle* h) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (h->gather_stream) CUDA_TRY(cudaStreamSynchronize(h->gather_stream));
+  comm_release(h);
+  return CASA_OK;
+}
+
+extern "C" int casa_allgather_points(casa_handle* h, void* nccl_comm, const float* local, float* gathered,
+                                     int64_t floats_per_rank, void* stream) {
+  if (!h || !local || !gathered) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (floats_per_rank < 0) return fail(CASA_ERR_INVALID, "floats_per_rank=%lld", (long long)floats_per_rank);
+  void* comm = nccl_comm ? nccl_comm : h->comm;
+  if (!comm) return fail(CASA_ERR_INVALID, "no communicator: call casa_comm_init / casa_comm_attach or pass an ncclComm_t");
+  int rc = nccl_load();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  NCCL_TRY(g_nccl.AllGather(local, gathered, (size_t)floats_per_rank, /* ncclFloat32 */ 7, comm, (cudaStream_t)stream));
+  return CASA_OK;
+}
+
+extern "C" int casa_allgather_points_overlapped(casa_handle* h, const float* local, float* gathered, int64_t floats_per_rank,
+                                                void* after_stream, int slot) {
+  if (!h || !local || !gathered) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (slot < 0 || slot >= 4) return fail(CASA_ERR_INVALID, "slot %d outside 0..3", slot);
+  if (!h->comm) return fail(CASA_ERR_INVALID, "no communicator: call casa_comm_init / casa_comm_attach first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->gather_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->gather_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->gather_after[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->gather_done[i], cudaEventDisableTiming));
+    }
+  }
+  // the gather stream waits only for what is queued on `after_stream` right now (the vote that produced `local`), so the
+  // exchange of step i overlaps the voting of step i + 1 and no compute stream ever waits for a peer
+  CUDA_TRY(cudaEventRecord(h->gather_after[slot], (cudaStream_t)after_stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->gather_stream, h->gather_after[slot], 0));
+  NCCL_TRY(g_nccl.AllGather(local, gathered, (size_t)floats_per_rank, 7, h->comm, h->gather_stream));
+  CUDA_TRY(cudaEventRecord(h->gather_done[slot], h->gather_stream));
+  return CASA_OK;
+}
+
+extern "C" int casa_gather_wait(casa_handle* h, int slot, void* stream) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (slot < 0 || slot >= 4 || !h->gather_done[slot]) return fail(CASA_ERR_INVALID, "slot %d has no gather in flight", slot);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (stream == (void*)-1)
+    CUDA_TRY(cudaEventSynchronize(h->gather_done[slot]));                       // host wait
+  else
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->gather_done[slot], 0));  // `stream` waits, the host does not
+  return CASA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ self tests
 
 extern "C" int casa_selftest_filter(casa_handle* h, uint64_t n, uint64_t seed, float inlier_thresh, float spread,
@@ -1088,54 +1243,15 @@ extern "C" int casa_selftest_filter(casa_handle* h, uint64_t n, uint64_t seed, f
 
 extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflops, double* ms_out) {
   if (!h || !tflops) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (variant != 0) return fail(CASA_ERR_INVALID, "casa_measure_fp32_peak: only variant 0 (FFMA issue rate) is part of the library");
   CUDA_TRY(cudaSetDevice(h->device));
   float* dout = nullptr;
   CUDA_TRY(cudaMalloc(&dout, 4));
-  // variant + 100*k limits residency to k blocks (8k warps) per SM through dynamic shared memory
-  const int occ_limit = variant / 100;
-  variant %= 100;
-  const size_t dsm = occ_limit > 0 ? (size_t)(220 * 1024 / occ_limit) & ~size_t(1023) : 0;
   const int iters = 8192, blocks = h->sm_count * 8;
   float best = 1e30f;
   for (int rep = 0; rep < 5; ++rep) {
     CUDA_TRY(cudaEventRecord(h->ev0, 0));
-    switch (variant) {
-      case 0: k_fma_peak<0><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 1: k_fma_peak<1><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 2: k_fma_peak<2><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 3:
-        if (dsm) CUDA_TRY(cudaFuncSetAttribute(k_fma_peak<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-        k_fma_peak<3><<<blocks, 256, dsm>>>(dout, iters, 1e-9f);
-        break;
-      case 10: k_fma_peak<10><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 11: k_fma_peak<11><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 12: k_fma_peak<12><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 13: k_fma_peak<13><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 14: k_fma_peak<14><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 15: k_fma_peak<15><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 16: k_fma_peak<16><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 17: k_fma_peak<17><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 18: k_fma_peak<18><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 20: k_fma_peak<20><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 21: k_fma_peak<21><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 22: k_fma_peak<22><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 23: k_fma_peak<23><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 24: k_fma_peak<24><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 25: k_fma_peak<25><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 26: k_fma_peak<26><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 27: k_fma_peak<27><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 28: k_fma_peak<28><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 29: k_fma_peak<29><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 30: k_fma_peak<30><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 31: k_fma_peak<31><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 40: k_fma_peak<40><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 50: k_fma_peak<50><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 51: k_fma_peak<51><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 52: k_fma_peak<52><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 53: k_fma_peak<53><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      case 54: k_fma_peak<54><<<blocks, 256>>>(dout, iters, 1e-9f); break;
-      default: return fail(CASA_ERR_INVALID, "unknown fp32 peak variant %d", variant);
-    }
+    k_fma_peak<<<blocks, 256>>>(dout, iters, 1e-9f);
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
     CUDA_TRY(cudaEventSynchronize(h->ev1));
     float ms = 0;
@@ -1143,10 +1259,7 @@ extern "C" int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflop
     if (rep > 0 && ms < best) best = ms;
   }
   CUDA_TRY(cudaFree(dout));
-  // variants 0-2: 16 FMA = 32 FLOP per thread-iteration; variant 3: 16 units x 11 algorithmic FLOP
-  // variant 50: 8 m16n8k8 MMAs per warp-iteration = 512 FLOP per thread; 51-53: 1024 units per warp-iteration
-  const double flop_per_iter = variant <= 2 ? 32.0 : variant == 50 ? 512.0 : variant >= 51 ? 32.0 * 11.0 : 16.0 * 11.0;
-  *tflops = (double)blocks * 256.0 * iters * flop_per_iter / (best * 1e-3) / 1e12;
+  *tflops = (double)blocks * 256.0 * iters * 32.0 / (best * 1e-3) / 1e12;  // 16 FMA = 32 FLOP per thread-iteration
   if (ms_out) *ms_out = best;
   return CASA_OK;
 }

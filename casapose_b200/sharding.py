@@ -92,59 +92,71 @@ class _StreamGather:
         return torch.cat([self._out[r * w : r * w + (e - s)] for r, (s, e) in enumerate(self._sizes)], dim=0)
 
 
-class GraphGather:
-    """The per-step keypoint all-gather as a replayed CUDA graph on a side stream.
+class AbiGather:
+    """The per-step keypoint all-gather through the library's C ABI (casa_comm_init / casa_allgather_points_overlapped):
+    NCCL is driven by the library, torch.distributed only carries the 128-byte NCCL id to the other ranks once
+    (any other channel would do: the reference's TensorFlow replicas have no torch process group).
 
-    The eager path costs the host about 75 us per step (c10d dispatch, allocation, work handle) — as much as the
-    9 KB exchange itself — and the voting loop is host-latency bound between steps.  Here the NCCL collective is
-    captured once per result buffer; a step then costs one stream-wait and one graph launch.  `slots` result
-    buffers alternate so the voting of step i + 1 never writes the buffer step i's gather still reads; the vote
-    writes straight into `buffer(i)` (its `out=` argument).  Every rank must construct and use it identically."""
+    The exchange runs on the handle's own gather stream behind the vote that produced the rows, so the gather of
+    step i overlaps the voting of step i + 1 and no compute stream ever waits for a peer.  `slots` result buffers
+    alternate; the vote of step i writes straight into `buffer(i)` (its `out=` argument)."""
 
-    def __init__(self, shape, device, world, stream, group=None, slots=2):
-        self.stream, self.world, self.group = stream, world, group
+    def __init__(self, shape, device, world, rank, group=None, slots=2):
+        import ctypes as C
+
+        from . import _lib
+
+        self.world, self.rank, self.device = world, rank, device
+        self.lib = _lib.lib()
+        self.hdl = _lib.handle(device.index, torch.cuda.current_stream(device).cuda_stream)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            _lib.check(self.lib.casa_nccl_unique_id(buf))
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if world > 1:
+            carrier = ident.to(device) if dist.get_backend(group) == "nccl" else ident
+            dist.broadcast(carrier, src=0, group=group)
+            ident = carrier.cpu()
+        raw = (C.c_char * 128).from_buffer_copy(ident.numpy().tobytes())
+        _lib.check(self.lib.casa_comm_init(self.hdl, raw, rank, world))
         self.inp = [torch.zeros(shape, dtype=torch.float32, device=device) for _ in range(slots)]
         self.out = [torch.zeros((world * shape[0],) + tuple(shape[1:]), dtype=torch.float32, device=device) for _ in range(slots)]
-        self.done = [torch.cuda.Event() for _ in range(slots)]
-        self.graphs = []
-        stream.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(stream):
-            for k in range(slots):  # eager warm-up: communicator set-up must not happen inside a capture
-                dist.all_gather_into_tensor(self.out[k], self.inp[k], group=group)
-        stream.synchronize()
-        for k in range(slots):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                dist.all_gather_into_tensor(self.out[k], self.inp[k], group=group)
-            self.graphs.append(g)
-        stream.synchronize()
         self.used = [False] * slots
+        self._check = _lib.check
 
     def buffer(self, step):
-        """Result tensor the vote of `step` must write; the compute stream first waits for the gather that last
-        read it (two steps ago: long finished, so the wait is free on the GPU)."""
+        """Result tensor the vote of `step` must write; the compute stream first waits (on the GPU) for the gather
+        that last read it — two steps ago, long finished."""
         k = step % len(self.inp)
         if self.used[k]:
-            torch.cuda.current_stream(self.inp[k].device).wait_event(self.done[k])
+            self._check(self.lib.casa_gather_wait(self.hdl, k, torch.cuda.current_stream(self.device).cuda_stream))
         return self.inp[k]
 
-    def launch(self, step, after):
-        """Queue the gather of `step` behind the event `after` (recorded right after its vote)."""
+    def launch(self, step):
+        """Queue the gather of `step` behind everything queued on the current stream (its vote)."""
         k = step % len(self.inp)
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(after)
-            self.graphs[k].replay()
-            self.done[k].record(self.stream)
+        self._check(self.lib.casa_allgather_points_overlapped(
+            self.hdl, self.inp[k].data_ptr(), self.out[k].data_ptr(), self.inp[k].numel(),
+            torch.cuda.current_stream(self.device).cuda_stream, k))
         self.used[k] = True
-        return _GraphGatherResult(self, k)
+        return _AbiGatherResult(self, k)
+
+    def barrier(self):
+        """Device-side barrier on the compute stream: an all-gather of the first result buffer."""
+        self._check(self.lib.casa_allgather_points(self.hdl, None, self.inp[0].data_ptr(), self.out[0].data_ptr(),
+                                                   self.inp[0].numel(), torch.cuda.current_stream(self.device).cuda_stream))
+
+    def close(self):
+        self._check(self.lib.casa_comm_destroy(self.hdl))
 
 
-class _GraphGatherResult:
+class _AbiGatherResult:
     def __init__(self, owner, k):
         self._owner, self._k = owner, k
 
     def wait(self):
-        self._owner.done[self._k].synchronize()
+        self._owner._check(self._owner.lib.casa_gather_wait(self._owner.hdl, self._k, -1))
         return self._owner.out[self._k]
 
 

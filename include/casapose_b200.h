@@ -208,7 +208,10 @@ int casa_pnp(casa_handle* h, int32_t n, int32_t vn, const float* points2d, const
  * map_estimates + evaluate_poses (/root/reference/casapose/pose_estimation/ransac_voting.py:561-625, 628-687):
  * per object one row [err_2d, err_3d, valid_3d, valid_2d, missing, false_positive]; the caller sums rows over
  * the batch like :668-675.  err_3d is the mean point distance (ADD) or, for models with 7862 / 3417 points
- * (:618), the mean closest-point distance from the float64 expansion of :596-610 (ADD-S).
+ * (:618), the mean closest-point distance (ADD-S).  The reference takes the closest point from the float64 expansion
+ * |a|^2 - 2ab + |b|^2 (:596-610); the kernel takes it from the direct float32 difference (a-b).(a-b), which has no
+ * cancellation (relative error 2e-7 of the squared distance): identical verdicts, errors within 1e-5 relative
+ * (tests/test_gpu_pose_metric.py).
  *   poses, poses_gt device float32 [n,3,4]            camera       device float32 [n,3,3]
  *   model_points    device float32 [m,maxp,3]         model_counts device int32   [m]  points used per model
  *   obj_model       device int32   [n] model of each object, or NULL: object i uses model i % m
@@ -235,6 +238,31 @@ int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t maxp, const f
  */
 int casa_set_async(casa_handle* h, int enable);
 int casa_sync(casa_handle* h);
+
+/*
+ * Multi-GPU: the path shards by image with no data-path collective (the reference maps independently over images,
+ * ransac_voting.py:483; its only multi-GPU mechanism, MirroredStrategy at train_casapose.py:195, shards the batch
+ * the same way); only the [b, oc, vn, 2] keypoints of every rank are all-gathered (576 B per frame).  The gather is
+ * part of the C ABI so that a caller without torch.distributed (a TensorFlow replica thread) can use it:
+ *   casa_nccl_unique_id   rank 0 creates the 128-byte NCCL id and distributes it by any means it has
+ *   casa_comm_init        every rank: ncclCommInitRank on the handle's device (owned by the handle)
+ *   casa_comm_attach      or borrow the framework's own ncclComm_t (never destroyed by this library)
+ *   casa_allgather_points ncclAllGather of `floats_per_rank` float32 per rank on `stream` (nccl_comm NULL: the handle's)
+ *   casa_allgather_points_overlapped  the same on the handle's own gather stream, ordered only behind what is queued
+ *                         on `after_stream` at the time of the call: the exchange of step i overlaps the voting of
+ *                         step i+1 and no compute stream ever waits for a peer; `slot` (0..3) names the completion
+ *                         event, casa_gather_wait(h, slot, stream) makes `stream` wait for it ((void*)-1: the host).
+ * NCCL is resolved with dlopen("libnccl.so.2") at the first call (CASA_NCCL_LIB overrides), so the library loads without it.
+ */
+int casa_nccl_unique_id(void* id128);
+int casa_comm_init(casa_handle* h, const void* id128, int rank, int world);
+int casa_comm_attach(casa_handle* h, void* nccl_comm, int rank, int world);
+int casa_comm_destroy(casa_handle* h);
+int casa_allgather_points(casa_handle* h, void* nccl_comm, const float* local, float* gathered, int64_t floats_per_rank,
+                          void* stream);
+int casa_allgather_points_overlapped(casa_handle* h, const float* local, float* gathered, int64_t floats_per_rank,
+                                     void* after_stream, int slot);
+int casa_gather_wait(casa_handle* h, int slot, void* stream);
 
 /* Device status word of the last casa_ransac_vote on this handle (CASA_STATUS_* bits). */
 int casa_last_status(casa_handle* h, uint32_t* status);
@@ -265,7 +293,9 @@ int casa_get_timing(casa_handle* h, double* score_ms, int64_t* score_launches, u
 int casa_selftest_filter(casa_handle* h, uint64_t n, uint64_t seed, float inlier_thresh,
                          float spread, uint64_t* out4_host);
 
-/* Measured FP32 FMA issue rate of this GPU (TFLOP/s), the denominator for "% of FP32 peak". */
+/* Measured FP32 FMA issue rate of this GPU (TFLOP/s), the denominator for "% of FP32 peak" (16 independent FFMA chains per
+ * thread, best of 4 timed launches).  variant must be 0; the instruction-mix explorations of round 1 are not part of the
+ * library any more (casapose_b200/csrc/experimental/). */
 int casa_measure_fp32_peak(casa_handle* h, int variant, double* tflops, double* ms);
 
 #ifdef __cplusplus

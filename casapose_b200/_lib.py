@@ -50,7 +50,7 @@ class LsParams(C.Structure):
     _fields_ = [
         ("b", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("num_classes", C.c_int32), ("vn", C.c_int32),
         ("sigmoid_weights", C.c_int32), ("filter_estimates", C.c_int32), ("second_largest", C.c_int32),
-        ("min_component", C.c_int32), ("check_finite", C.c_int32),
+        ("min_component", C.c_int32), ("check_finite", C.c_int32), ("pix_capacity", C.c_int32),
     ]
 
 
@@ -69,6 +69,8 @@ EXPORTS = {
                                    C.c_void_p, C.c_void_p, C.POINTER(RansacDebug), C.c_void_p]),
     "casa_ransac_vote_seg": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.POINTER(RansacDebug), C.c_void_p]),
+    "casa_ransac_vote_dlpack": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p]),
     "casa_ransac_vote_host": (C.c_int, [C.c_void_p, C.POINTER(RansacParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "casa_ls_vote": (C.c_int, [C.c_void_p, C.POINTER(LsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.POINTER(LsDebug), C.c_void_p]),

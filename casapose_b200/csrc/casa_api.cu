@@ -75,6 +75,7 @@ struct casa_handle {
   int comm_owned = 0, comm_rank = 0, comm_world = 1;
   cudaStream_t gather_stream = nullptr;
   cudaEvent_t gather_after[4] = {nullptr, nullptr, nullptr, nullptr}, gather_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* deferred_list = nullptr;  // std::vector<DeferredDelete>*: consumed DLPack capsules whose deleters are pending
   CallSlot slots[kCallSlots];
   char* slot_mem = nullptr;       // page-locked backing store of the slots' read-back buffers
   int64_t slot_head = 0, slot_tail = 0;  // calls issued / calls collected (pending = head - tail)
@@ -141,6 +142,11 @@ int nccl_load() {
 
 struct casa_handle;
 static void comm_release(casa_handle* h);
+static void run_deferred(casa_handle* h, bool wait);
+namespace {
+struct DeferredDelete;
+}
+static std::vector<DeferredDelete>& deferred(casa_handle* h);
 
 extern "C" int casa_version(void) { return CASA_VERSION; }
 extern "C" const char* casa_last_error(void) { return g_err; }
@@ -190,6 +196,10 @@ extern "C" int casa_destroy(casa_handle* h) {
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
     delete g;
+  }
+  if (h->deferred_list) {
+    run_deferred(h, true);
+    delete &deferred(h);
   }
   comm_release(h);
   if (h->gather_stream) cudaStreamDestroy(h->gather_stream);
@@ -784,6 +794,131 @@ extern "C" int casa_ransac_vote_seg(casa_handle* h, const casa_ransac_params* p,
   return ransac_vote_impl(h, p, seg, 1, vertex, idxs, selection, out_points, debug, stream);
 }
 
+// ------------------------------------------------------------------------------------------------ DLPack shim
+// The reference hands tensors to foreign code through tf.numpy_function (ransac_voting.py:513, bpnp_layers.py:322);
+// the drop-in's seam is DLPack: any framework's tensor arrives as a DLManagedTensor* (the pointer inside the
+// "dltensor" PyCapsule), is validated HERE — device, dtype, shape, strides — and consumed exactly once.
+namespace {
+// DLPack ABI (dlpack.h, v0.x layout; public standard, restated so that the library has no header dependency)
+struct DLDevice {
+  int32_t device_type;  // 2 = kDLCUDA, 13 = kDLCUDAManaged
+  int32_t device_id;
+};
+struct DLDataType {
+  uint8_t code;  // 2 = kDLFloat
+  uint8_t bits;
+  uint16_t lanes;
+};
+struct DLTensor {
+  void* data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides;  // NULL = compact row-major
+  uint64_t byte_offset;
+};
+struct DLManagedTensor {
+  DLTensor dl_tensor;
+  void* manager_ctx;
+  void (*deleter)(DLManagedTensor*);
+};
+
+int check_dl(const DLManagedTensor* m, const char* name, int device, int ndim_a, int ndim_b) {
+  if (!m) return fail(CASA_ERR_INVALID, "%s: DLManagedTensor is NULL", name);
+  const DLTensor& t = m->dl_tensor;
+  if (t.device.device_type != 2 && t.device.device_type != 13)
+    return fail(CASA_ERR_INVALID, "%s: DLPack device type %d is not CUDA", name, t.device.device_type);
+  if (t.device.device_id != device) return fail(CASA_ERR_INVALID, "%s lives on CUDA device %d, the handle on %d", name, t.device.device_id, device);
+  if (t.dtype.code != 2 || t.dtype.bits != 32 || t.dtype.lanes != 1)
+    return fail(CASA_ERR_INVALID, "%s must be float32 (DLPack dtype code %d, %d bits, %d lanes)", name, t.dtype.code, t.dtype.bits, t.dtype.lanes);
+  if (t.ndim != ndim_a && t.ndim != ndim_b) return fail(CASA_ERR_INVALID, "%s has %d dimensions", name, t.ndim);
+  if (!t.data || !t.shape) return fail(CASA_ERR_INVALID, "%s: NULL data / shape", name);
+  if (t.strides) {  // must be compact row-major (NHWC like the reference's tensors): no silent copies
+    int64_t expect = 1;
+    for (int i = t.ndim - 1; i >= 0; --i) {
+      if (t.shape[i] != 1 && t.strides[i] != expect) return fail(CASA_ERR_INVALID, "%s is not C-contiguous (stride %lld of dimension %d)", name, (long long)t.strides[i], i);
+      expect *= t.shape[i];
+    }
+  }
+  return CASA_OK;
+}
+
+const float* dl_data(const DLManagedTensor* m) { return (const float*)((const char*)m->dl_tensor.data + m->dl_tensor.byte_offset); }
+
+struct DeferredDelete {
+  DLManagedTensor* m;
+  cudaEvent_t done;
+};
+}  // namespace
+
+// deleters of consumed capsules run once the GPU work that reads them has finished (polled at later API calls)
+static std::vector<DeferredDelete>& deferred(casa_handle* h) {
+  if (!h->deferred_list) h->deferred_list = new std::vector<DeferredDelete>();
+  return *(std::vector<DeferredDelete>*)h->deferred_list;
+}
+static void run_deferred(casa_handle* h, bool wait) {
+  std::vector<DeferredDelete>& v = deferred(h);
+  for (size_t i = 0; i < v.size();) {
+    if (wait) cudaEventSynchronize(v[i].done);
+    if (wait || cudaEventQuery(v[i].done) == cudaSuccess) {
+      if (v[i].m->deleter) v[i].m->deleter(v[i].m);
+      bool shared = false;
+      for (size_t k = 0; k < v.size(); ++k) shared |= k != i && v[k].done == v[i].done;
+      if (!shared) cudaEventDestroy(v[i].done);
+      v.erase(v.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+}
+
+extern "C" int casa_ransac_vote_dlpack(casa_handle* h, const casa_ransac_params* p, void* mask_dlm, void* vertex_dlm, void* out_dlm,
+                                       int mask_is_seg, void* stream) {
+  if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
+  run_deferred(h, false);
+  DLManagedTensor* m = (DLManagedTensor*)mask_dlm;
+  DLManagedTensor* v = (DLManagedTensor*)vertex_dlm;
+  DLManagedTensor* o = (DLManagedTensor*)out_dlm;
+  auto reject = [&](int code) {  // the capsules are consumed in every case: a rejected call releases them at once
+    if (m && m->deleter) m->deleter(m);
+    if (v && v->deleter) v->deleter(v);
+    if (o && o->deleter) o->deleter(o);
+    return code;
+  };
+  int rc = check_dl(m, mask_is_seg ? "seg" : "mask", h->device, 4, 4);
+  if (!rc) rc = check_dl(v, "vertex", h->device, 5, 6);
+  if (!rc) rc = check_dl(o, "out", h->device, 4, 4);
+  if (rc) return reject(rc);
+  casa_ransac_params q = *p;  // shapes come from the tensors themselves
+  const int64_t* ms = m->dl_tensor.shape;
+  const int64_t* vs = v->dl_tensor.shape;
+  const int64_t* os = o->dl_tensor.shape;
+  q.b = (int32_t)ms[0];
+  q.h = (int32_t)ms[1];
+  q.w = (int32_t)ms[2];
+  q.oc = (int32_t)ms[3] - (mask_is_seg ? 1 : 0);
+  q.vertex_per_class = v->dl_tensor.ndim == 6;
+  q.vn = (int32_t)vs[v->dl_tensor.ndim - 2];
+  if (vs[0] != ms[0] || vs[1] != ms[1] || vs[2] != ms[2] || vs[v->dl_tensor.ndim - 1] != 2 || (q.vertex_per_class && vs[3] != q.oc))
+    return reject(fail(CASA_ERR_INVALID, "vertex must be [b,h,w,vn,2] or [b,h,w,oc,vn,2] matching the mask"));
+  if (os[0] != q.b || os[1] != q.oc || os[2] != q.vn || os[3] != 2) return reject(fail(CASA_ERR_INVALID, "out must be [b,oc,vn,2]"));
+  rc = ransac_vote_impl(h, &q, dl_data(m), mask_is_seg, dl_data(v), nullptr, nullptr, (float*)dl_data(o), nullptr, stream);
+  // the capsules are consumed either way: their deleters run once the work queued so far on `stream` has finished
+  cudaEvent_t done = nullptr;
+  if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess && cudaEventRecord(done, (cudaStream_t)stream) == cudaSuccess) {
+    deferred(h).push_back({m, done});
+    deferred(h).push_back({v, done});
+    deferred(h).push_back({o, done});
+  } else {
+    cudaStreamSynchronize((cudaStream_t)stream);
+    if (m->deleter) m->deleter(m);
+    if (v->deleter) v->deleter(v);
+    if (o->deleter) o->deleter(o);
+  }
+  return rc;
+}
+
 // true if `p` is page-locked host memory the device can read directly (UVA: same pointer)
 static bool host_pointer_is_mapped(const void* p, const void** dev_ptr) {
   cudaPointerAttributes at;
@@ -886,7 +1021,7 @@ struct LsGrad {
   float* grad_conf = nullptr;          // [b,h,w,vn]
 };
 int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct, const float* conf,
-                 float* out_points, const casa_ls_debug* debug, void* stream, const LsGrad* grad);
+                 float* out_points, const casa_ls_debug* debug, void* stream, const LsGrad* grad, int pix_capacity = 0);
 }  // namespace
 
 extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct,
@@ -911,13 +1046,17 @@ extern "C" int casa_ls_vote_backward(casa_handle* h, const casa_ls_params* p, co
 
 namespace {
 int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, const float* direct, const float* conf,
-                 float* out_points, const casa_ls_debug* debug, void* stream, const LsGrad* grad) {
+                 float* out_points, const casa_ls_debug* debug, void* stream, const LsGrad* grad, int pix_capacity) {
   if (p->num_classes < 2 || p->num_classes > 33) return fail(CASA_ERR_INVALID, "num_classes=%d outside 2..33", p->num_classes);
   casa_ransac_params rp;
   memset(&rp, 0, sizeof(rp));
   rp.b = p->b; rp.h = p->h; rp.w = p->w; rp.oc = p->num_classes - 1; rp.vn = p->vn;
   rp.round_hyp_num = 1; rp.max_iter = 1;
   rp.min_num = 0.f; rp.max_num = 3.0e38f; rp.inlier_thresh = 0.99f; rp.confidence = 0.99f;
+  // A pixel is listed for every class whose softmax(1e6 seg) value is non-zero, so near-tied logits (flat regions, a
+  // zero-initialised seg head) can list a pixel several times: the per-image list then needs more than h*w slots.
+  // The first attempt uses h*w (or the caller's pix_capacity); an overflow is retried below with the measured need.
+  rp.pix_capacity = pix_capacity > 0 ? pix_capacity : p->pix_capacity;
   Layout L;
   int rc = make_layout(&rp, L);
   if (rc) return rc;
@@ -983,7 +1122,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   steps.push_back(kstep((const void*)k_ls_weights, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(conf));
   steps.push_back(kstep((const void*)k_ls_reduce, dim3(grid_x, d.vn), 256).arg(ws).arg(d).arg(lw).arg(ld));
   if (!out_points) out_points = (float*)(base + off_tmp_out);
-  steps.push_back(kstep((const void*)k_ls_solve, d.J, 32).arg(ws).arg(d).arg(ld).arg(out_points).arg(dbg.sums));
+  steps.push_back(kstep((const void*)k_ls_solve, d.J, 32).arg(ws).arg(d).arg(ld).arg(out_points).arg(dbg.sums).arg(h->sticky));
   if (grad) {
     float* adj = (float*)(base + off_adj);
     CUDA_TRY(cudaMemsetAsync(grad->grad_direct, 0, npx * 2 * d.vn * sizeof(float), st));
@@ -1000,11 +1139,29 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   if (dbg.selected && ld.filter) CUDA_TRY(cudaMemcpyAsync(dbg.selected, lw.sel, (size_t)d.J * 4, cudaMemcpyDeviceToDevice, st));
   if (dbg.tn) CUDA_TRY(cudaMemcpyAsync(dbg.tn, ws.job_tn, (size_t)d.J * 4, cudaMemcpyDeviceToDevice, st));
   h->last_launches = launches;
-  if (p->check_finite) {
+  h->last_stream = st;
+  if (p->check_finite || grad) {  // the backward pass always checks for a list overflow (it would zero gradients silently)
     CUDA_TRY(cudaMemcpyAsync(h->pinned, ws.ctrl, CTRL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     h->last_status = (uint32_t)h->pinned[CTRL_STATUS];
-    if (h->last_status & CASA_STATUS_LS_NONFINITE)
+    if (h->last_status & CASA_STATUS_PIX_OVERFLOW) {
+      // measured need: the largest per-image sum of the class counts (the reference has no such limit: it evaluates
+      // every class on the dense field, voting_layers_2d.py:107-114)
+      std::vector<int> tn0(d.J);
+      CUDA_TRY(cudaMemcpy(tn0.data(), ws.job_tn0, (size_t)d.J * sizeof(int), cudaMemcpyDeviceToHost));
+      long long need = 0;
+      for (int i = 0; i < d.b; ++i) {
+        long long sum = 0;
+        for (int c = 0; c < d.oc; ++c) sum += tn0[(size_t)i * d.oc + c];
+        need = sum > need ? sum : need;
+      }
+      need = (need + 1023) / 1024 * 1024;
+      CUDA_TRY(cudaMemset(h->sticky, 0, sizeof(uint32_t)));  // the retried call reports for itself
+      if (need <= d.cap || need > (1ll << 30))
+        return fail(CASA_ERR_WORKSPACE, "CoordLSVotingWeighted: pixel lists overflow (need %lld slots per image)", need);
+      return ls_vote_impl(h, p, seg, direct, conf, out_points == (float*)(base + off_tmp_out) ? nullptr : out_points, debug, stream, grad, (int)need);
+    }
+    if (p->check_finite && (h->last_status & CASA_STATUS_LS_NONFINITE))
       return fail(CASA_ERR_INPUT, "CoordLSVotingWeighted: non-finite R / q / p (the reference asserts here, voting_layers_2d.py:109-121)");
   }
   return CASA_OK;
@@ -1085,6 +1242,7 @@ extern "C" int casa_sync(casa_handle* h) {
   CUDA_TRY(cudaSetDevice(h->device));
   int rc = collect(h);
   CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+  if (h->deferred_list) run_deferred(h, true);
   CUDA_TRY(cudaMemcpy(h->pinned_sticky, h->sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   const uint32_t st = *h->pinned_sticky;
   if (st) CUDA_TRY(cudaMemset(h->sticky, 0, sizeof(uint32_t)));
@@ -1092,6 +1250,7 @@ extern "C" int casa_sync(casa_handle* h) {
   if (st & CASA_STATUS_PIX_OVERFLOW)
     return fail(CASA_ERR_WORKSPACE, "a call since the last casa_sync overflowed its pixel lists (mask not one-hot?); retry with a larger pix_capacity");
   if (st & CASA_STATUS_IDX_RANGE) return fail(CASA_ERR_INPUT, "a call since the last casa_sync had caller-supplied idxs outside [0, tn)");
+  if (st & CASA_STATUS_LS_NONFINITE) return fail(CASA_ERR_INPUT, "a CoordLSVotingWeighted call since the last casa_sync produced non-finite R / q / p");
   return CASA_OK;
 }
 

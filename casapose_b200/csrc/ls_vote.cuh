@@ -516,8 +516,12 @@ __device__ __forceinline__ void pinv2x2_apply(double a, double b, double c, doub
 }
 
 // one warp per job, lane v = keypoint
-__global__ void __launch_bounds__(32) k_ls_solve(WS ws, Dims d, LsDims ld, float* __restrict__ out, double* dbg_sums) {
+__global__ void __launch_bounds__(32) k_ls_solve(WS ws, Dims d, LsDims ld, float* __restrict__ out, double* dbg_sums, uint32_t* sticky) {
   const int job = blockIdx.x, v = threadIdx.x;
+  if (job == 0 && v == 0 && sticky) {  // a pixel-list overflow (raised by k_job_tables) must not stay silent: -> casa_sync
+    const unsigned st = (unsigned)ws.ctrl[CTRL_STATUS] & CASA_STATUS_PIX_OVERFLOW;
+    if (st) atomicOr(sticky, st);
+  }
   if (v >= d.vn) return;
   const int r0 = ws.rtile_start[job], r1 = ws.rtile_start[job + 1];
   double acc[5] = {0, 0, 0, 0, 0};
@@ -531,7 +535,10 @@ __global__ void __launch_bounds__(32) k_ls_solve(WS ws, Dims d, LsDims ld, float
 #pragma unroll
   for (int k = 0; k < 5; ++k) bad |= !(fabs(acc[k]) <= 1.7e308);
   bad |= !(fabsf(o0) <= 3.4e38f) || !(fabsf(o1) <= 3.4e38f);
-  if (bad) atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), LS_STATUS_NONFINITE);
+  if (bad) {
+    atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), LS_STATUS_NONFINITE);
+    if (sticky) atomicOr(sticky, LS_STATUS_NONFINITE);
+  }
   reinterpret_cast<float2*>(out)[(size_t)job * d.vn + v] = make_float2(o0, o1);  // (y, x) pixels
   if (dbg_sums)
 #pragma unroll

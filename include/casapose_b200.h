@@ -159,7 +159,11 @@ typedef struct casa_ls_params {
   int32_t filter_estimates;  /* keep only the selected connected component (:43-79)         */
   int32_t second_largest;    /* output_second_largest_component (:58-73)                    */
   int32_t min_component;     /* 0 = the reference's 50 (:66)                                */
-  int32_t check_finite;
+  int32_t check_finite;      /* 1: synchronise, raise on non-finite results (the reference's tf.Assert :109-121) and retry   */
+                             /*    a pixel-list overflow with the measured capacity; 0: fully asynchronous, both conditions */
+                             /*    are reported by casa_sync                                                                */
+  int32_t pix_capacity;      /* slots per image of the pixel lists; 0 = h*w.  A pixel is listed once per class whose        */
+                             /* softmax(1e6 seg) is non-zero, so near-tied logits need more than h*w (up to oc*h*w)         */
 } casa_ls_params;
 
 typedef struct casa_ls_debug {
@@ -238,6 +242,20 @@ int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t maxp, const f
  */
 int casa_set_async(casa_handle* h, int enable);
 int casa_sync(casa_handle* h);
+
+/*
+ * DLPack entry point: the same vote with the tensors handed over as DLManagedTensor* (the pointer inside a "dltensor"
+ * PyCapsule produced by any framework's __dlpack__: TensorFlow's tf.experimental.dlpack.to_dlpack, CuPy, JAX, PyTorch).
+ * This is the drop-in's counterpart of the reference's only foreign-code seam, tf.numpy_function
+ * (ransac_voting.py:513, bpnp_layers.py:322).  Device type, device id, float32 dtype, dimensions and C-contiguous
+ * strides are validated here, in C; b, h, w, oc, vn and vertex_per_class are taken from the tensors (the other fields of
+ * `p` are used as given); `out` is a caller-allocated [b,oc,vn,2] tensor of the same device.  The three capsules are
+ * CONSUMED in every case: their deleters are called exactly once — at once if the call is rejected, otherwise when the
+ * GPU work queued on `stream` by this call has finished (polled at later calls on the handle, casa_sync, casa_destroy).
+ * mask_is_seg != 0: `mask` holds [b,h,w,1+oc] segmentation scores (casa_ransac_vote_seg).
+ */
+int casa_ransac_vote_dlpack(casa_handle* h, const casa_ransac_params* p, void* mask_dlm, void* vertex_dlm, void* out_dlm,
+                            int mask_is_seg, void* stream);
 
 /*
  * Multi-GPU: the path shards by image with no data-path collective (the reference maps independently over images,

@@ -106,3 +106,23 @@ def test_non_finite_input_raises_like_the_reference_assert(Layer):
     layer = Layer("ls", 2, num_points=2)
     with pytest.raises(CasaError):
         layer([torch.from_numpy(seg).cuda(), torch.from_numpy(direct).cuda(), torch.from_numpy(conf).cuda()])
+
+
+def test_tied_logits_list_a_pixel_for_every_class(Layer):
+    """All-equal segmentation logits (a zero-initialised seg head): softmax(1e6 * seg) is 1/nc for EVERY class, so each
+    pixel is listed oc times and the per-image lists need oc*h*w slots — the layer must give the reference's weighted
+    solution (weights 1/nc), not zeros (the first attempt at h*w slots overflows and is retried with the measured need);
+    the backward pass must see the same lists."""
+    rng = np.random.default_rng(11)
+    b, h, w, nc, vn = 2, 24, 32, 5, 3
+    seg = np.zeros((b, h, w, nc), np.float32)
+    ang = rng.uniform(0, 2 * np.pi, (b, h, w, vn))
+    direct = np.stack([np.sin(ang), np.cos(ang)], -1).reshape(b, h, w, 2 * vn).astype(np.float32)
+    conf = rng.normal(size=(b, h, w, vn)).astype(np.float32)
+    out, dbg, ref, _ = _run(Layer, seg, direct, conf)
+    assert (dbg["tn"].cpu().numpy() == h * w).all()
+    assert np.abs(ref).max() > 1.0  # a real solution, not the zeros of a gated class
+    layer = Layer("ls", nc, num_points=vn)
+    g = torch.ones((b, nc - 1, vn, 2), device="cuda")
+    gd, gw = layer.backward([torch.from_numpy(seg).cuda(), torch.from_numpy(direct).cuda(), torch.from_numpy(conf).cuda()], g)
+    assert float(gd.abs().max()) > 0 and float(gw.abs().max()) > 0

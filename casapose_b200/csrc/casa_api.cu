@@ -1108,7 +1108,8 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   }
   steps.push_back(kstep((const void*)k_job_tables, d.b, 256).arg(ws).arg(d));
   steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
-  steps.push_back(kstep((const void*)k_plan, 1, 256).arg(ws).arg(d).arg((int)0));
+  // topology: the work-item / tile plan only needs the job table and runs beside the component chain (side branch)
+  steps.push_back(kstep((const void*)k_plan, 1, d.J > 256 ? 1024 : 256).arg(ws).arg(d).arg((int)0).on_side(1));
   const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
   if (ld.filter) {
     steps.push_back(kstep((const void*)k_cc_init, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld));
@@ -1117,10 +1118,15 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
     steps.push_back(kstep((const void*)k_cc_select, d.J, 256).arg(lw).arg(ld));
   }
   const int grid_x = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
-  steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gx, d.J), 256)
-                      .arg(direct).arg(ws).arg(d));
-  steps.push_back(kstep((const void*)k_ls_weights, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(conf));
-  steps.push_back(kstep((const void*)k_ls_reduce, dim3(grid_x, d.vn), 256).arg(ws).arg(d).arg(lw).arg(ld));
+  if (grad) {
+    // the backward pass reads the gathered directions / weights / confidences: the three-kernel form fills them
+    steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gx, d.J), 256)
+                        .arg(direct).arg(ws).arg(d).joins());
+    steps.push_back(kstep((const void*)k_ls_weights, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(conf));
+    steps.push_back(kstep((const void*)k_ls_reduce, dim3(grid_x, d.vn), 256).arg(ws).arg(d).arg(lw).arg(ld));
+  } else {
+    steps.push_back(kstep((const void*)k_ls_fused, grid_x, 32 * d.vn).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(direct).arg(conf).joins());
+  }
   if (!out_points) out_points = (float*)(base + off_tmp_out);
   steps.push_back(kstep((const void*)k_ls_solve, d.J, 32).arg(ws).arg(d).arg(ld).arg(out_points).arg(dbg.sums).arg(h->sticky));
   if (grad) {

@@ -479,6 +479,109 @@ __global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDim
   }
 }
 
+// Forward pass without intermediates: weights, direction gather and the weighted reduction in ONE pass over the
+// pixel lists.  blockIdx.x strides over the 1024-pixel tiles of the jobs, one warp per keypoint (block = 32 * vn).
+//   phase 1 (all threads): weight = hot_seg * component mask of the tile's pixels (:39-41, :72-79) -> shared memory;
+//   phase 2 (warp v):      keypoint v over the tile; the pixel's direction (8 bytes of its 72-byte row) and
+//                          confidence logit are read straight from the dense network outputs — the rows of a tile
+//                          are touched by all vn warps of the block back to back, so they cross HBM once — and
+//                          go through the reference's float32 element-wise sequence (:89-108) into float64 sums.
+// Replaces k_gather_dirs + k_ls_weights + k_ls_reduce (102 us of launches and 140 MB of intermediates per 16 frames)
+// for the forward call; the backward pass still uses the gathered arrays.
+__global__ void __launch_bounds__(512, 2) k_ls_fused(WS ws, Dims d, LsWS lw, LsDims ld, const float* __restrict__ seg,
+                                                  const float* __restrict__ direct, const float* __restrict__ conf) {
+  const int tid = threadIdx.x, lane = tid & 31, v = tid >> 5;
+  const int n_rtiles = ws.rtile_start[d.J];
+  __shared__ float s_w[kRefineTile];
+  __shared__ uint32_t s_pix[kRefineTile];
+  __shared__ float2 s_c[kRefineTile];  // grid position (cy, cx) = ((y+.5)/H, (x+.5)/H): one pair of divisions per pixel
+  const float fh = (float)ld.h;
+  for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
+    const int job = ws.rtile_job[rt], tile = rt - ws.rtile_start[job];
+    const int tn = ws.job_tn[job];
+    const int img = job / d.oc, c = job - img * d.oc;
+    const size_t base = (size_t)img * d.cap + ws.job_off[job];
+    const int sel = ld.filter ? lw.sel[job] : 0;
+    const int npx = min(kRefineTile, tn - tile * kRefineTile);
+    __syncthreads();  // the previous tile's readers are done with s_w / s_pix
+    for (int k = tid; k < npx; k += blockDim.x) {
+      const uint32_t pk = ws.pix[base + (size_t)tile * kRefineTile + k];
+      const int x = pk & 0xFFFFu, y = pk >> 16;
+      const size_t p = (size_t)img * ld.hw + (size_t)y * ld.w + x;
+      float row[33];
+      for (int q = 0; q < ld.nc; ++q) row[q] = __ldg(seg + p * ld.nc + q);
+      float w = hot_of_row(row, ld.nc, c + 1);  // hot_seg (:39-41)
+      if (ld.filter) {                          // copy_components * hot_seg (:72-79)
+        const int c9 = lw.cls9[p];
+        const bool keep = sel == -2 ? (c9 != c + 1) : (sel >= 0 && c9 == c + 1 && lw.parent[p] == sel);
+        w = __fmul_rn(keep ? 1.0f : 0.0f, w);
+      }
+      s_w[k] = w;
+      s_pix[k] = pk;
+      s_c[k] = make_float2(__fdiv_rn(__fadd_rn((float)y, 0.5f), fh), __fdiv_rn(__fadd_rn((float)x, 0.5f), fh));  // :96-97
+    }
+    __syncthreads();
+    double s[5] = {0, 0, 0, 0, 0};
+    constexpr int kBatch = 8;  // pixels per lane whose loads are in flight together (the loop is latency-bound otherwise)
+    for (int k0 = 0; k0 < npx; k0 += 32 * kBatch) {
+      float bw[kBatch], bc[kBatch];
+      uint32_t bp[kBatch];
+      float2 bd[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int k = k0 + j * 32 + lane;
+        bw[j] = k < npx ? s_w[k] : 0.f;
+        bp[j] = k < npx ? s_pix[k] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        bd[j] = make_float2(0.f, 0.f);
+        bc[j] = 0.f;
+        if (bw[j] != 0.f) {
+          const size_t p = (size_t)img * ld.hw + (size_t)(bp[j] >> 16) * ld.w + (bp[j] & 0xFFFFu);
+          bd[j] = __ldg(reinterpret_cast<const float2*>(direct + p * (size_t)(2 * d.vn)) + v);  // (n0, n1) = (dy, dx)
+          bc[j] = __ldg(conf + p * (size_t)d.vn + v);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const float w = bw[j];
+        if (w == 0.f) continue;  // multiply_no_nan (:107-108); also slots past the end of the tile
+        const float2 dv = bd[j];
+        const float wc = ls_weight(bc[j], ld.sigmoid_weights);                                  // :32-35
+        const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dv.x, dv.x), __fmul_rn(dv.y, dv.y)));  // :89
+        const float n0 = nrm != 0.f ? __fdiv_rn(dv.x, nrm) : 0.f;  // divide_no_nan :90
+        const float n1 = nrm != 0.f ? __fdiv_rn(dv.y, nrm) : 0.f;
+        const float r00 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n0, n0)), wc);  // :92-94
+        const float r01 = __fmul_rn(__fsub_rn(0.0f, __fmul_rn(n0, n1)), wc);
+        const float r11 = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(n1, n1)), wc);
+        const float2 g = s_c[k0 + j * 32 + lane];  // (w != 0 implies the slot is inside the tile)
+        const float cy = g.x, cx = g.y;            // both axes over the height (:96-97)
+        const float q0 = __fadd_rn(__fmul_rn(r00, cy), __fmul_rn(r01, cx));  // :103-105
+        const float q1 = __fadd_rn(__fmul_rn(r01, cy), __fmul_rn(r11, cx));
+        s[0] += (double)__fmul_rn(r00, w);  // :108, :113
+        s[1] += (double)__fmul_rn(r01, w);
+        s[2] += (double)__fmul_rn(r11, w);
+        s[3] += (double)__fmul_rn(q0, w);   // :107, :114
+        s[4] += (double)__fmul_rn(q1, w);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    }
+    if (lane < 5) {
+      double t = s[0];  // every lane holds all five sums after the xor tree
+      t = lane == 1 ? s[1] : t;
+      t = lane == 2 ? s[2] : t;
+      t = lane == 3 ? s[3] : t;
+      t = lane == 4 ? s[4] : t;
+      ws.partial[((size_t)rt * d.vn + v) * 5 + lane] = t;
+    }
+  }
+}
+
 // Moore-Penrose inverse of the symmetric [[a,b],[b,c]] applied to (g0,g1); singular values below
 // rcond * max are dropped (tf.linalg.pinv default rcond = 10 * 2 * eps_f64, :116)
 __device__ __forceinline__ void pinv2x2_apply(double a, double b, double c, double g0, double g1, double& p0, double& p1) {

@@ -35,8 +35,8 @@ H, W, OC, VN, HN, BATCH = 480, 640, 8, 9, 512, 16
 FLOP_PER_UNIT = 11
 METRIC = "keypoint-voting frames/s (480x640, 8 obj x 9 kp, 512 hyp)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch on this workload,
-# from profiles/r01_k_score_full.txt (ncu --set full); null until a capture exists
-K_SCORE_DRAM_BYTES = 54.1e6
+# from profiles/r02_k_score_full.txt (ncu --set full: 53.44 MB read + 0.79 MB written)
+K_SCORE_DRAM_BYTES = 54.2e6
 
 
 def parse():

@@ -495,10 +495,16 @@ def main():
             torch.cuda.synchronize()
             h2d_gbs = max(h2d_gbs, mask_h.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
         del scratch
-        moved_bytes = mask_h.numel() * 4 + float(mask_h.sum()) * 2 * vn * 4
+        # the host entry splits the batch into image ranges (4 for b >= 8, 2 for b >= 2): even ranges cross PCIe as raw
+        # floats, odd ranges as one host-packed u32 per pixel (casa_ransac_vote_host); CASA_NO_HOST_PACK=1 moves all raw
+        parts = 4 if B >= 8 else (2 if B >= 2 else 1)
+        packed_imgs = 0 if os.environ.get("CASA_NO_HOST_PACK") else sum(
+            B * (k + 1) // parts - B * k // parts for k in range(parts) if k & 1)
+        px = h_ * w_
+        moved_bytes = (B - packed_imgs) * px * oc * 4 + packed_imgs * px * 4 + float(mask_h.sum()) * 2 * vn * 4
         e2e = {"value": n_images * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
                "d2h_bytes_per_step": B * oc * vn * 2 * 4, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-               "h2d_gbs_measured": h2d_gbs, "bytes_moved_per_step": moved_bytes,
+               "h2d_gbs_measured": h2d_gbs, "bytes_moved_per_step": moved_bytes, "host_packed_images": packed_imgs,
                "pcie_floor_ms": moved_bytes / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None}
 
     if rank == 0:

@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("CASA_LIB_PATH") or os.path.join(CSRC, "libcasapose_b200.so")  # override: A/B runs only
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-ldl",
+    "-shared", "-Xcompiler", "-fPIC", "-ldl", "-lpthread",
 ]
 
 STATUS_BITS = {

@@ -1,11 +1,16 @@
 // C ABI of casapose_b200 (include/casapose_b200.h): host-side orchestration of the kernels.
 // Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 #include <dlfcn.h>
+#include <immintrin.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -35,6 +40,139 @@ static int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess)                                                                   \
       return fail(CASA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+
+// ------------------------------------------------------------------------------------------------ host mask packer
+// casa_ransac_vote_host: the float one-hot mask carries 4 bits of information per 32 bytes.  A small pool of host
+// threads turns it into one u32 membership word per pixel (the same word k_mask_bits builds on the device) while
+// the GPU works on the previous image range, so 1/8 of the mask's bytes (1/oc in general) cross PCIe.
+namespace {
+class MaskPacker {
+ public:
+  explicit MaskPacker(int n) : n_(n) {
+    for (int i = 0; i < n_; ++i) workers_.emplace_back([this, i] { run(i); });
+  }
+  ~MaskPacker() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (std::thread& t : workers_) t.join();
+  }
+  // packs `mask` ([npx][oc] floats) into `bits`; part k = pixels [bounds[2k], bounds[2k+1]), parts in order
+  void start(const float* mask, uint32_t* bits, int oc, const std::vector<size_t>& bounds) {
+    std::lock_guard<std::mutex> g(m_);
+    mask_ = mask;
+    bits_ = bits;
+    oc_ = oc;
+    bounds_ = bounds;
+    done_.assign(bounds.size() / 2, 0);
+    not_binary_.store(0);
+    ++epoch_;
+    cv_.notify_all();
+  }
+  void wait_part(size_t k) {
+    std::unique_lock<std::mutex> g(m_);
+    cv_done_.wait(g, [&] { return done_[k] == n_; });
+  }
+  int not_binary() const { return not_binary_.load(); }
+
+ private:
+  void run(int id) {
+    long long seen = 0;
+    for (;;) {
+      std::vector<size_t> bounds;
+      const float* mask;
+      uint32_t* bits;
+      int oc;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return quit_ || epoch_ != seen; });
+        if (quit_) return;
+        seen = epoch_;
+        bounds = bounds_;
+        mask = mask_;
+        bits = bits_;
+        oc = oc_;
+      }
+      for (size_t k = 0; 2 * k + 1 < bounds.size(); ++k) {  // every worker takes its slice of every part, parts in order
+        const size_t n = bounds[2 * k + 1] - bounds[2 * k];
+        const size_t lo = bounds[2 * k] + n * id / n_, hi = bounds[2 * k] + n * (id + 1) / n_;
+        if (pack(mask, bits, oc, lo, hi)) not_binary_.store(1);
+        {
+          std::lock_guard<std::mutex> g(m_);
+          ++done_[k];
+        }
+        cv_done_.notify_all();
+      }
+    }
+  }
+  // bit c of bits[p] = (mask[p][c] != 0) — NaN counts as set, -0 does not, like tf.not_equal (:304); returns whether a
+  // set element differs from 1.0 (CASA_STATUS_MASK_NOT_BINARY)
+  __attribute__((target("avx2"))) static bool pack8_avx2(const float* mask, uint32_t* bits, size_t lo, size_t hi) {
+    // one 256-bit row per pixel: (v << 1) != 0 per lane -> 8-bit membership word; set lanes must hold 1.0f
+    const __m256i zero = _mm256_setzero_si256(), one = _mm256_set1_epi32(0x3F800000);
+    unsigned bad = 0;
+    for (size_t p = lo; p < hi; ++p) {
+      const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(mask + 8 * p));
+      const unsigned z = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(_mm256_slli_epi32(v, 1), zero)));
+      const unsigned e1 = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(v, one)));
+      const unsigned m = ~z & 0xFFu;
+      bad |= m & ~e1;
+      bits[p] = m;
+    }
+    return bad != 0;
+  }
+  static bool pack(const float* mask, uint32_t* bits, int oc, size_t lo, size_t hi) {
+    bool bad = false;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(mask);
+    if (oc == 8 && __builtin_cpu_supports("avx2")) return pack8_avx2(mask, bits, lo, hi);
+    if (oc == 8) {  // 32 bytes per pixel, all-zero rows (background) leave after four 64-bit tests
+      const uint64_t* q = reinterpret_cast<const uint64_t*>(mask);
+      for (size_t p = lo; p < hi; ++p) {
+        const uint64_t a = q[4 * p], b = q[4 * p + 1], c = q[4 * p + 2], e = q[4 * p + 3];
+        uint32_t m = 0;
+        if ((a | b | c | e) != 0) {
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t v = w[8 * p + k];
+            if ((v << 1) != 0u) {
+              m |= 1u << k;
+              bad |= v != 0x3F800000u;
+            }
+          }
+        }
+        bits[p] = m;
+      }
+      return bad;
+    }
+    for (size_t p = lo; p < hi; ++p) {
+      uint32_t m = 0;
+      for (int k = 0; k < oc; ++k) {
+        const uint32_t v = w[p * oc + k];
+        if ((v << 1) != 0u) {
+          m |= 1u << k;
+          bad |= v != 0x3F800000u;
+        }
+      }
+      bits[p] = m;
+    }
+    return bad;
+  }
+
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, cv_done_;
+  bool quit_ = false;
+  long long epoch_ = 0;
+  const float* mask_ = nullptr;
+  uint32_t* bits_ = nullptr;
+  int oc_ = 0;
+  std::vector<size_t> bounds_;
+  std::vector<int> done_;
+  std::atomic<int> not_binary_{0};
+};
+}  // namespace
 
 // Read-back slot of one call: the loop state, the statistics and the events of a call live in their own slot of a ring,
 // so that asynchronous callers can queue calls back to back and collect them later (casa_sync / casa_get_timing).
@@ -76,6 +214,10 @@ struct casa_handle {
   cudaStream_t gather_stream = nullptr;
   cudaEvent_t gather_after[4] = {nullptr, nullptr, nullptr, nullptr}, gather_done[4] = {nullptr, nullptr, nullptr, nullptr};
   void* deferred_list = nullptr;  // std::vector<DeferredDelete>*: consumed DLPack capsules whose deleters are pending
+  int host_not_binary = 0;        // the host packer saw a mask value other than 0 / 1 in the current call
+  MaskPacker* packer = nullptr;   // host threads of casa_ransac_vote_host
+  uint32_t* bits_host = nullptr;  // page-locked staging of the packed membership words
+  size_t bits_host_bytes = 0;
   CallSlot slots[kCallSlots];
   char* slot_mem = nullptr;       // page-locked backing store of the slots' read-back buffers
   int64_t slot_head = 0, slot_tail = 0;  // calls issued / calls collected (pending = head - tail)
@@ -197,6 +339,8 @@ extern "C" int casa_destroy(casa_handle* h) {
     if (g->graph) cudaGraphDestroy(g->graph);
     delete g;
   }
+  delete h->packer;
+  if (h->bits_host) cudaFreeHost(h->bits_host);
   if (h->deferred_list) {
     run_deferred(h, true);
     delete &deferred(h);
@@ -727,7 +871,9 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
   }
-  if (mask_is_seg)
+  if (mask_is_seg == 2)  // membership words packed on the host (casa_ransac_vote_host); bit 30 of the flag: not binary
+    steps.push_back(kstep((const void*)k_bits_in, dim3(d.nct, d.b), 256).arg((const uint32_t*)mask).arg(ws).arg(d).arg(h->host_not_binary));
+  else if (mask_is_seg)
     steps.push_back(kstep((const void*)k_seg_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d));
   else
     steps.push_back(kstep((const void*)k_mask_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d).arg(vec4));
@@ -955,8 +1101,14 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   // pixels' rows straight from the mapped host buffer.  About 200 MB instead of 511 MB cross PCIe for a 16-frame
   // batch, and the voting hides behind the mask transfer.  Pageable buffers are staged in one piece.
   const void *dm = nullptr, *dv = nullptr;
-  const bool zero_copy = !getenv("CASA_NO_ZERO_COPY") && host_pointer_is_mapped(mask_host, &dm) && host_pointer_is_mapped(vertex_host, &dv);
-  const size_t mask_b = (mask_n + 255) & ~size_t(255);
+  const bool vertex_mapped = !getenv("CASA_NO_ZERO_COPY") && host_pointer_is_mapped(vertex_host, &dv);
+  const bool mask_mapped = host_pointer_is_mapped(mask_host, &dm);
+  // host-side packing of the mask (any host memory: the CPU reads it) needs the vector field to be readable in place
+  const bool pack = vertex_mapped && !getenv("CASA_NO_HOST_PACK") && p->oc <= 32;
+  const bool zero_copy = vertex_mapped && (pack || mask_mapped);
+  const size_t bits_n = (size_t)p->b * hw * sizeof(uint32_t);
+  const size_t bits_b = pack ? (bits_n + 255) & ~size_t(255) : 0;
+  const size_t mask_b = ((mask_n + 255) & ~size_t(255)) + bits_b;  // raw float ranges, then the packed words
   const size_t vert_b = zero_copy ? 0 : (vert_n + 255) & ~size_t(255);
   rc = ensure(&h->io_mem, &h->io_bytes, mask_b + vert_b + out_b);
   if (rc) return rc;
@@ -977,7 +1129,41 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     const size_t mask_img = hw * p->oc, vert_img = hw * vfields * p->vn * 2, out_img = (size_t)p->oc * p->vn * 2;
     int start[9];
     for (int k = 0; k <= parts; ++k) start[k] = (int)((long long)p->b * k / parts);
-    for (int k = 0; k < parts; ++k) {  // all mask copies are queued up front on the copy stream
+    // The one-hot mask is 32 bytes per pixel for 4 bits of information.  Two engines move it in parallel: the copy
+    // engine DMA-copies the raw floats of the even image ranges over PCIe, host threads (MaskPacker) turn the odd
+    // ranges into u32 membership words — 1/oc of the bytes — while the GPU votes on the ranges before them.
+    // (Packing everything on the host is no faster than the DMA on a 16-core host: profiles/r02_e2e.txt.)
+    uint32_t* dbits = (uint32_t*)((char*)h->io_mem + mask_b - bits_b);
+    bool packed[9] = {false, false, false, false, false, false, false, false, false};
+    int pack_index[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (pack) {
+      if (!h->packer) {
+        int n = (int)std::thread::hardware_concurrency() - 1;
+        if (getenv("CASA_HOST_THREADS")) n = atoi(getenv("CASA_HOST_THREADS"));
+        n = n < 1 ? 1 : (n > 8 ? 8 : n);  // more lose to oversubscription on a 16-core host
+        h->packer = new MaskPacker(n);
+      }
+      if (h->bits_host_bytes < bits_n) {
+        if (h->bits_host) CUDA_TRY(cudaFreeHost(h->bits_host));
+        h->bits_host = nullptr;
+        h->bits_host_bytes = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&h->bits_host, bits_n, cudaHostAllocDefault));
+        h->bits_host_bytes = bits_n;
+      }
+      const bool all = getenv("CASA_HOST_PACK_ALL") != nullptr || !mask_mapped;  // a pageable mask cannot be DMA-copied in place
+      std::vector<size_t> bounds;
+      for (int k = 0; k < parts; ++k) {
+        packed[k] = all || (k & 1);
+        if (packed[k]) {
+          pack_index[k] = (int)bounds.size() / 2;
+          bounds.push_back((size_t)start[k] * hw);
+          bounds.push_back((size_t)start[k + 1] * hw);
+        }
+      }
+      h->packer->start(mask_host, h->bits_host, p->oc, bounds);
+    }
+    for (int k = 0; k < parts; ++k) {  // the raw ranges are queued up front on the copy stream
+      if (packed[k]) continue;
       const size_t o = (size_t)start[k] * mask_img, n = (size_t)(start[k + 1] - start[k]) * mask_img;
       CUDA_TRY(cudaMemcpyAsync(dmask + o, mask_host + o, n * 4, cudaMemcpyHostToDevice, h->copy_stream));
       CUDA_TRY(cudaEventRecord(h->part_ev[k], h->copy_stream));
@@ -991,10 +1177,26 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       casa_ransac_params pp = *p;
       pp.b = start[k + 1] - start[k];
       pp.image_offset = p->image_offset + start[k];
+      if (packed[k]) {
+        h->packer->wait_part((size_t)pack_index[k]);
+        const size_t o = (size_t)start[k] * hw, n = (size_t)pp.b * hw;
+        CUDA_TRY(cudaMemcpyAsync(dbits + o, h->bits_host + o, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->copy_stream));
+        CUDA_TRY(cudaEventRecord(h->part_ev[k], h->copy_stream));
+        h->host_not_binary = h->packer->not_binary();
+      }
       CUDA_TRY(cudaStreamWaitEvent(st, h->part_ev[k], 0));
-      rc = casa_ransac_vote(h, &pp, dmask + (size_t)start[k] * mask_img, (const float*)dv + (size_t)start[k] * vert_img,
-                            nullptr, nullptr, dout + (size_t)start[k] * out_img, nullptr, (void*)st);
-      if (rc) return rc;
+      if (packed[k])
+        rc = ransac_vote_impl(h, &pp, (const float*)(dbits + (size_t)start[k] * hw), 2, (const float*)dv + (size_t)start[k] * vert_img,
+                              nullptr, nullptr, dout + (size_t)start[k] * out_img, nullptr, (void*)st);
+      else
+        rc = casa_ransac_vote(h, &pp, dmask + (size_t)start[k] * mask_img, (const float*)dv + (size_t)start[k] * vert_img,
+                              nullptr, nullptr, dout + (size_t)start[k] * out_img, nullptr, (void*)st);
+      if (rc) {
+        if (pack)
+          for (int j = k + 1; j < parts; ++j)
+            if (packed[j]) h->packer->wait_part((size_t)pack_index[j]);  // the workers still read the caller's buffer
+        return rc;
+      }
       launches += h->last_launches;
       score_ms += h->score_ms;
       score_launches += h->score_launches;

@@ -97,6 +97,37 @@ __global__ void __launch_bounds__(256) k_mask_bits(const float* __restrict__ mas
   if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
 }
 
+// Membership words that were packed on the host (casa_ransac_vote_host): same outputs as k_mask_bits — ws.bits and
+// the per-tile class counts — from one u32 per pixel instead of oc floats.
+__global__ void __launch_bounds__(256) k_bits_in(const uint32_t* __restrict__ src, WS ws, Dims d, int not_binary) {
+  const int img = blockIdx.y, tile = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int scnt[32];
+  if (tid < 32) scnt[tid] = 0;
+  __syncthreads();
+  uint32_t m[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = tile * kCountTile + k * 256 + tid;
+    m[k] = p < d.hw ? __ldg(src + (size_t)img * d.hw + p) : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = tile * kCountTile + k * 256 + tid;
+    if (p < d.hw) ws.bits[(size_t)img * d.hw + p] = m[k];
+    if (__any_sync(0xffffffffu, m[k] != 0u)) {
+      for (int c = 0; c < d.oc; ++c) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (m[k] >> c) & 1u);
+        if (lane == 0 && bal) atomicAdd(&scnt[c], __popc(bal));
+      }
+    }
+  }
+  if (not_binary && tile == 0 && img == 0 && tid == 0)
+    atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_MASK_NOT_BINARY);
+  __syncthreads();
+  if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
+}
+
 // Fused pre-step (pose_evaluation.py:36-47): bit c of a pixel is set iff argmax(seg) == c + 1
 // (tf.argmax takes the first maximum; NaN scores never win, like Eigen's comparison-based arg-max).
 __global__ void __launch_bounds__(256) k_seg_bits(const float* __restrict__ seg, WS ws, Dims d) {

@@ -233,3 +233,18 @@ def test_host_buffer_entry_point_matches_device_path(vote):
     dev = vote(torch.from_numpy(d["mask"]).cuda(), torch.from_numpy(d["vertex"]).cuda(), 64, seed=4)
     host = ransac_voting_layer_all_masks_host(torch.from_numpy(d["mask"]).pin_memory(), torch.from_numpy(d["vertex"]).pin_memory(), 64, seed=4)
     assert torch.equal(dev.cpu(), host)
+
+
+def test_host_entry_packs_a_pageable_mask_beside_a_pinned_vertex_field(vote):
+    """The host entry packs the mask into membership words on host threads (any host memory) and reads the vector
+    field in place (pinned): 8 classes take the 64-bit fast path of the packer, batch 9 splits into 4 image ranges."""
+    from casapose_b200.pose_estimation.ransac_voting import ransac_voting_layer_all_masks_host
+
+    d = synthetic.make_frames(3, 96, 128, synthetic.CONFIG_8_IDS, variant="easy")
+    mask = np.tile(d["mask"], (3, 1, 1, 1))
+    vertex = np.tile(d["vertex"], (3, 1, 1, 1, 1))
+    dev = vote(torch.from_numpy(mask).cuda(), torch.from_numpy(vertex).cuda(), 64, seed=9)
+    host = ransac_voting_layer_all_masks_host(torch.from_numpy(mask), torch.from_numpy(vertex).pin_memory(), 64, seed=9)
+    assert torch.equal(dev.cpu(), host)
+    again = ransac_voting_layer_all_masks_host(torch.from_numpy(mask), torch.from_numpy(vertex).pin_memory(), 64, seed=9)
+    assert torch.equal(host, again)

@@ -50,6 +50,7 @@ def parse():
                     help="BASELINE.json config: 2 (default, the headline), 3 (13 objects, batch 32), 4 (batch 256 sharded: strong scaling), 5 (1080x1920, --hn sweep)")
     ap.add_argument("--hn", type=int, default=None, help="hypotheses per round (config 5 sweep: 128 .. 2048)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3, help="calls in flight in the timed region (casa_set_async); 1 = one lane")
     ap.add_argument("--variant", default="easy")
     ap.add_argument("--cpu-sample-frames", type=int, default=None,
                     help="frames of the batch the CPU restatement is timed on (default: 8 for the cpu_baseline leg = about 8 s, 1 per step for --impl reference)")
@@ -369,10 +370,12 @@ def main():
     # The keypoints of a step ([B,oc,9,2], 576 B per frame at oc = 8) are all-gathered with NCCL through the library's
     # own C-ABI gather (casa_allgather_points_overlapped) on a gather stream that waits only for that step's vote,
     # so the exchange overlaps the next step's voting; every gather completes inside the timed region.
-    gather = sharding.AbiGather((B, oc, vn, 2), dev, world, rank) if distributed else None
     if distributed and cfg["scaling"] == "strong" and total_batch % world:
         raise SystemExit("config 4 needs a batch divisible by the number of GPUs")
+    lanes = max(1, min(4, args.lanes))
+    gather = sharding.AbiGather((B, oc, vn, 2), dev, world, rank, slots=max(2, 2 * lanes)) if distributed else None
     counter = [0]
+    outs = [torch.empty((B, oc, vn, 2), dtype=torch.float32, device=dev) for _ in range(8)]  # results of the calls in flight
 
     class _Done:
         def __init__(self, v):
@@ -382,10 +385,10 @@ def main():
             return self.v
 
     def step(seed):
-        if not distributed:
-            return _Done(ransac_voting_layer_all_masks(mask, vertex, hn, seed=seed, image_offset=start_img))
         i = counter[0]
         counter[0] += 1
+        if not distributed:
+            return _Done(ransac_voting_layer_all_masks(mask, vertex, hn, seed=seed, image_offset=start_img, out=outs[i % 8]))
         ransac_voting_layer_all_masks(mask, vertex, hn, seed=seed, image_offset=start_img, out=gather.buffer(i))
         return gather.launch(i)
 
@@ -404,45 +407,67 @@ def main():
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    # asynchronous calls: the library enqueues ONE CUDA graph per step (device-driven RANSAC loop) and returns; the
-    # steps queue back to back on the GPU, their loop states / statistics / k_score events are collected at the end
+    # Asynchronous calls: the library enqueues ONE CUDA graph per step (device-driven RANSAC loop) and returns; loop
+    # states / statistics / k_score events are collected at the end.  The timed region that gives `value` runs with
+    # `lanes` calls in flight (casa_set_async(h, lanes): consecutive votes rotate over that many workspaces / streams, so
+    # the latency-bound compaction and refinement kernels of neighbouring steps overlap and the k_score launches run back
+    # to back).  k_score's own duration is timed in a second pass of the same K steps on ONE lane, where an event pair
+    # around the kernel measures the kernel: with several lanes a launch queues behind the previous lane's k_score and
+    # the pair would include that wait.
+    stream_ptr = torch.cuda.current_stream(dev).cuda_stream
     sampler = ClockSampler(local)
     sampler.start()  # started before the warm-up so that NVML is initialised when the timed region begins
-    _lib.check(lib.casa_set_async(hdl, 1))
-    for it in range(max(args.warmup, 3)):
-        step(it).wait()
-    _lib.check(lib.casa_sync(hdl))
-    barrier()
 
-    # --- timed region: K steps, device-resident inputs
-    _lib.check(lib.casa_set_timing(hdl, 1))
-    sm, sl, st = C.c_double(), C.c_int64(), (C.c_uint64 * 4)()
-    nl = C.c_int64()
-    lib.casa_last_launches(hdl, C.byref(nl))
-    lib.casa_get_timing(hdl, C.byref(sm), C.byref(sl), st)  # drop the warm-up totals
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if distributed:
-        gather.barrier()  # device-side barrier on the compute stream: the ranks enter the timed region together
-    sampler.mark()
-    e0.record()
-    pending = None
-    for it in range(args.steps):
-        nxt = step(1000 + it)
-        if pending is not None and it % 16 == 0:
-            pending.wait()  # host-side check-point: the gathered keypoints of an earlier step are complete
-        pending = nxt
-    gathered = pending.wait()
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    _lib.check(lib.casa_sync(hdl))
-    lib.casa_last_launches(hdl, C.byref(nl))  # asynchronous handle: total over the calls since the last query
-    lib.casa_get_timing(hdl, C.byref(sm), C.byref(sl), st)
-    score_ms, score_launches, launches, units, exact_units = sm.value, sl.value, nl.value, st[0], st[1]
+    def timed_pass(mode, timing, sample):
+        _lib.check(lib.casa_set_async(hdl, mode))
+        _lib.check(lib.casa_set_timing(hdl, 0))
+        for it in range(max(args.warmup, 3)):
+            step(it).wait()
+        if mode >= 2:
+            _lib.check(lib.casa_join(hdl, stream_ptr))
+        _lib.check(lib.casa_sync(hdl))
+        barrier()
+        _lib.check(lib.casa_set_timing(hdl, timing))
+        sm, sl, st = C.c_double(), C.c_int64(), (C.c_uint64 * 4)()
+        nl = C.c_int64()
+        lib.casa_last_launches(hdl, C.byref(nl))
+        lib.casa_get_timing(hdl, C.byref(sm), C.byref(sl), st)  # drop the warm-up totals
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if distributed:
+            gather.barrier()  # device-side barrier on the compute stream: the ranks enter the timed region together
+        if sample:
+            sampler.mark()
+        e0.record()
+        pending = None
+        for it in range(args.steps):
+            nxt = step(1000 + it)
+            if pending is not None and it % 16 == 0:
+                pending.wait()  # host-side check-point: the gathered keypoints of an earlier step are complete
+            pending = nxt
+        last = pending.wait()
+        if mode >= 2:
+            _lib.check(lib.casa_join(hdl, stream_ptr))  # the caller's stream waits for every lane
+        e1.record()
+        barrier()
+        clk = sampler.stop() if sample else None
+        _lib.check(lib.casa_sync(hdl))
+        lib.casa_last_launches(hdl, C.byref(nl))  # asynchronous handle: total over the calls since the last query
+        lib.casa_get_timing(hdl, C.byref(sm), C.byref(sl), st)
+        _lib.check(lib.casa_set_timing(hdl, 0))
+        return dict(ms=e0.elapsed_time(e1), score_ms=sm.value, score_launches=sl.value, launches=nl.value,
+                    units=st[0], exact_units=st[1], last=last, clocks=clk)
+
+    main_pass = timed_pass(lanes if lanes >= 2 else 1, 0 if lanes >= 2 else 1, True)
+    kern_pass = timed_pass(1, 1, False) if lanes >= 2 else main_pass
     _lib.check(lib.casa_set_async(hdl, 0))
-    _lib.check(lib.casa_set_timing(hdl, 0))
-    elapsed_ms = e0.elapsed_time(e1)
+    clocks = main_pass["clocks"]
+    gathered = main_pass["last"]
+    score_ms, score_launches = kern_pass["score_ms"], kern_pass["score_launches"]
+    launches, units, exact_units = main_pass["launches"], main_pass["units"], main_pass["exact_units"]
+    one_lane_ms = kern_pass["ms"] / args.steps
+    kern_elapsed_ms = kern_pass["ms"]
+    elapsed_ms = main_pass["ms"]
     gather_ok = None
     if distributed:
         # EVERY row of the last step's gathered tensor is checked: each rank recomputes the other ranks' keypoints
@@ -534,6 +559,8 @@ def main():
                 "parallelism": "images sharded across ranks (same seeded frames on every rank, distinct global image indices), NCCL all-gather of the [b,%d,9,2] keypoints through the C-ABI gather on the library's gather stream, every gathered row verified: %s" % (
                     oc, gather_ok) if distributed else "single GPU",
                 "exact_fallback_fraction": exact_units / units if units else None,
+                "calls_in_flight": lanes,
+                "ms_per_step_one_lane": one_lane_ms,
             },
             "clocks": clocks,
             "gpu_launches": launches_all,
@@ -544,6 +571,9 @@ def main():
                 "peak_source": "FFMA micro-kernel of this library measured in this run (MEASURED_PEAKS.json has no FP32 figure); nominal 74.5 TFLOP/s at 1965 MHz",
                 "launch_ms": score_ms / score_launches if score_launches else None,
                 "launches_timed": score_launches,
+                "timed_in": ("a second pass of the same %d steps with one call in flight (event pair around the kernel; with %d lanes a "
+                             "launch queues behind the previous lane's k_score and the pair would include the wait)" % (args.steps, lanes))
+                            if lanes >= 2 else "the timed region itself",
                 "share_of_step": score_ms / elapsed_ms if elapsed_ms else None,
                 "frame_frac": (t_fp32_ms + t_hbm_ms) / step_ms if step_ms else None,
                 "frame_model": {"t_fp32_ms": t_fp32_ms, "t_hbm_ms": t_hbm_ms, "alg_bytes_per_step": alg_bytes,

@@ -81,6 +81,7 @@ EXPORTS = {
     "casa_pose_errors": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "casa_set_async": (C.c_int, [C.c_void_p, C.c_int]),
+    "casa_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "casa_sync": (C.c_int, [C.c_void_p]),
     "casa_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "casa_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
@@ -168,7 +169,12 @@ def handle(device, stream=0):
 def set_async(device, enable, stream=0):
     """Asynchronous calls on this (device, thread, stream) handle: consecutive votes queue back to back on the GPU;
     `sync(device)` waits for them and raises the first error any of them hit (casa_set_async / casa_sync)."""
-    check(lib().casa_set_async(handle(device, stream), 1 if enable else 0))
+    check(lib().casa_set_async(handle(device, stream), int(enable)))
+
+
+def join(device, stream=0):
+    """Two-lane mode (set_async(device, 2)): orders every vote issued so far on `stream` (casa_join)."""
+    check(lib().casa_join(handle(device, stream), C.c_void_p(stream)))
 
 
 def sync(device, stream=0):

@@ -184,6 +184,7 @@ struct CallSlot {
   int64_t base_launches = 0, round_launches = 0;
 };
 constexpr int kCallSlots = 256;
+constexpr int kMaxLanes = 4;
 
 struct casa_handle {
   int device = 0;
@@ -212,8 +213,9 @@ struct casa_handle {
   void* comm = nullptr;           // ncclComm_t
   int comm_owned = 0, comm_rank = 0, comm_world = 1;
   cudaStream_t gather_stream = nullptr;
-  cudaEvent_t gather_after[4] = {nullptr, nullptr, nullptr, nullptr}, gather_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t gather_after[8] = {}, gather_done[8] = {};
   void* deferred_list = nullptr;  // std::vector<DeferredDelete>*: consumed DLPack capsules whose deleters are pending
+  int vertex_mapped = 0;          // the current call's vector field is mapped host memory (casa_ransac_vote_host)
   int host_not_binary = 0;        // the host packer saw a mask value other than 0 / 1 in the current call
   MaskPacker* packer = nullptr;   // host threads of casa_ransac_vote_host
   uint32_t* bits_host = nullptr;  // page-locked staging of the packed membership words
@@ -224,6 +226,16 @@ struct casa_handle {
   cudaStream_t last_stream = nullptr;
   const void* clean_ctrl = nullptr;  // address of the ctrl / stats words the previous vote's graph left zeroed (layouts move them)
   int async_mode = 0;             // 1: casa_ransac_vote returns without waiting for the loop state (casa_sync collects errors)
+                                  // n = 2..4: as 1, and consecutive votes rotate over n lanes (below)
+  // Lanes (casa_set_async(h, n)): n sub-handles with their own workspace and stream.  Vote i runs on lane i % n behind
+  // an event recorded on the caller's stream, so the compaction / hypothesis kernels and the refinements of n votes
+  // overlap (they are latency-bound; the k_score launches run back to back, each filling the GPU on its own).  Outputs
+  // are ordered on a caller's stream by casa_join(), on the host by casa_sync().
+  casa_handle* lane[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_fork[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr}, lane_done[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  int lane_pending[kMaxLanes] = {0, 0, 0, 0};
+  int lane_next = 0, lane_last = -1;
+  int is_lane = 0;
   uint32_t* sticky = nullptr;     // device word: OR of the status words of every call since the last casa_sync
   uint32_t* pinned_sticky = nullptr;
   std::vector<struct casa_graph*> graphs;
@@ -236,6 +248,8 @@ struct casa_graph {
   std::vector<cudaGraphNode_t> knodes;  // kernel nodes in list order (top level and WHILE body alike)
   cudaGraphConditionalHandle cond = 0;  // condition of the graph's WHILE node (0: the list has no loop)
   cudaGraphNode_t ev0_node = nullptr, ev1_node = nullptr, evr_node = nullptr, ctrl_node = nullptr, stats_node = nullptr;
+  std::vector<std::vector<char>> last_args;  // argument bytes each kernel node currently holds: unchanged nodes are not patched
+  const void* last_slot = nullptr;           // read-back slot the event / copy nodes currently point at
 };
 
 // ------------------------------------------------------------------------------------------------ NCCL (dlopen)
@@ -339,6 +353,12 @@ extern "C" int casa_destroy(casa_handle* h) {
     if (g->graph) cudaGraphDestroy(g->graph);
     delete g;
   }
+  for (int i = 0; i < kMaxLanes; ++i) {
+    if (h->lane[i]) casa_destroy(h->lane[i]);
+    if (h->lane_fork[i]) cudaEventDestroy(h->lane_fork[i]);
+    if (h->lane_done[i]) cudaEventDestroy(h->lane_done[i]);
+  }
+  cudaSetDevice(h->device);
   delete h->packer;
   if (h->bits_host) cudaFreeHost(h->bits_host);
   if (h->deferred_list) {
@@ -347,7 +367,7 @@ extern "C" int casa_destroy(casa_handle* h) {
   }
   comm_release(h);
   if (h->gather_stream) cudaStreamDestroy(h->gather_stream);
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     if (h->gather_after[i]) cudaEventDestroy(h->gather_after[i]);
     if (h->gather_done[i]) cudaEventDestroy(h->gather_done[i]);
   }
@@ -381,7 +401,7 @@ namespace {
 
 struct Layout {
   Dims d;
-  size_t off_bits, off_tile_cnt, off_tile_base, off_pix, off_vdir, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
+  size_t off_bits, off_tile_cnt, off_pix, off_vdir, off_job_tn0, off_job_tn, off_job_off, off_job_flags,
       off_job_rounds, off_job_done, off_job_selthr, off_win_ratio, off_win_pts, off_hyp_true, off_hyp_filt, off_exact_list,
       off_n_exact, off_counts, off_item_start, off_rtile_start, off_rtile_job, off_rtile_rec, off_ctrl, off_partial, off_stats, total;
 };
@@ -426,7 +446,6 @@ int make_layout(const casa_ransac_params* p, Layout& L) {
   const size_t J = d.J, jv = J * d.vn, jvh = jv * d.hn;
   L.off_bits = bump(cur, (size_t)d.b * d.hw * 4);
   L.off_tile_cnt = bump(cur, J * d.nct * 4);
-  L.off_tile_base = bump(cur, J * d.nct * 4);
   L.off_pix = bump(cur, (size_t)d.b * d.cap * 4);
   L.off_vdir = bump(cur, (size_t)d.b * d.cap * d.vn * 8);
   L.off_job_tn0 = bump(cur, J * 4);
@@ -459,7 +478,6 @@ WS make_ws(const Layout& L, void* base, bool stats) {
   WS w;
   w.bits = (uint32_t*)(b + L.off_bits);
   w.tile_cnt = (int*)(b + L.off_tile_cnt);
-  w.tile_base = (int*)(b + L.off_tile_base);
   w.pix = (uint32_t*)(b + L.off_pix);
   w.vdir = (float2*)(b + L.off_vdir);
   w.job_tn0 = (int*)(b + L.off_job_tn0);
@@ -527,14 +545,17 @@ struct Step {
   int cond_arg = -1;  // index of the argument that receives the graph's WHILE condition handle (k_update)
   // graph topology: 0 = main chain; 1 = opens a side branch off the main chain's last node; 2 = continues the side
   // branch.  join: this main-chain step also waits for the side branch (which ends there).
+  // Two side branches can be open at a time (slot 0 and slot 1).
   int side = 0;
-  bool join = false;
-  Step& on_side(int v) {
+  int slot = 0;
+  bool join = false, join1 = false;
+  Step& on_side(int v, int sl = 0) {
     side = v;
+    slot = sl;
     return *this;
   }
-  Step& joins() {
-    join = true;
+  Step& joins(int sl = 0) {
+    (sl ? join1 : join) = true;
     return *this;
   }
   template <class T>
@@ -665,16 +686,17 @@ static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cud
     for (const Step& s : steps) has_loop |= s.kind == STEP_WHILE_BEGIN;
     if (has_loop) CUDA_TRY(cudaGraphConditionalHandleCreate(&g->cond, g->graph, 0, cudaGraphCondAssignDefault));
     cudaGraph_t cur = g->graph;
-    cudaGraphNode_t prev = nullptr, side_prev = nullptr, loop_node = nullptr;
+    cudaGraphNode_t prev = nullptr, side_prev[2] = {nullptr, nullptr}, loop_node = nullptr;
     for (Step& s : steps) {
       cudaGraphNode_t node = nullptr;
-      cudaGraphNode_t deps[2];
+      cudaGraphNode_t deps[3];
       size_t nd = 0;
       if (s.side == 2) {
-        if (side_prev) deps[nd++] = side_prev;
+        if (side_prev[s.slot]) deps[nd++] = side_prev[s.slot];
       } else {
         if (prev) deps[nd++] = prev;
-        if (s.join && side_prev) deps[nd++] = side_prev;
+        if (s.side == 0 && s.join && side_prev[0]) deps[nd++] = side_prev[0];
+        if (s.side == 0 && s.join1 && side_prev[1]) deps[nd++] = side_prev[1];
       }
       cudaGraphNode_t* dep = nd ? deps : nullptr;
       switch (s.kind) {
@@ -685,6 +707,7 @@ static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cud
           kparams(s, args, kp);
           CUDA_TRY(cudaGraphAddKernelNode(&node, cur, dep, nd, &kp));
           g->knodes.push_back(node);
+          g->last_args.emplace_back(s.buf, s.buf + s.used);
           break;
         }
         case STEP_EV0:
@@ -722,23 +745,25 @@ static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cud
           CUDA_TRY(cudaGraphAddNode(&loop_node, cur, dep, nd, &cp));
           cur = cp.conditional.phGraph_out[0];
           prev = nullptr;
-          side_prev = nullptr;
+          side_prev[0] = side_prev[1] = nullptr;
           continue;
         }
         case STEP_WHILE_END:
           cur = g->graph;
           prev = loop_node;
-          side_prev = nullptr;
+          side_prev[0] = side_prev[1] = nullptr;
           continue;
       }
       if (s.side == 0) {
         prev = node;
-        if (s.join) side_prev = nullptr;
+        if (s.join) side_prev[0] = nullptr;
+        if (s.join1) side_prev[1] = nullptr;
       } else {
-        side_prev = node;
+        side_prev[s.slot] = node;
       }
     }
     CUDA_TRY(cudaGraphInstantiate(&g->exec, g->graph, 0));
+    g->last_slot = slot;
     if (h->graphs.size() >= 16) {  // tiny cache: drop the oldest shape
       casa_graph* old = h->graphs.front();
       cudaGraphExecDestroy(old->exec);
@@ -752,12 +777,19 @@ static int run_graph(casa_handle* h, std::vector<Step>& steps, const WS& ws, cud
     for (Step& s : steps) {
       if (s.kind != STEP_KERNEL) continue;
       s.set_cond((unsigned long long)g->cond);
+      std::vector<char>& held = g->last_args[k];
+      if (held.size() == s.used && memcmp(held.data(), s.buf, s.used) == 0) {  // same arguments as the node holds
+        ++k;
+        continue;
+      }
+      held.assign(s.buf, s.buf + s.used);
       void* args[8];
       cudaKernelNodeParams kp;
       kparams(s, args, kp);
       CUDA_TRY(cudaGraphExecKernelNodeSetParams(g->exec, g->knodes[k++], &kp));
     }
-    if (slot) {  // this call's read-back slot
+    if (slot && g->last_slot != (const void*)slot) {  // this call's read-back slot
+      g->last_slot = slot;
       if (g->ev0_node) CUDA_TRY(cudaGraphExecEventRecordNodeSetEvent(g->exec, g->ev0_node, slot->ev0));
       if (g->ev1_node) CUDA_TRY(cudaGraphExecEventRecordNodeSetEvent(g->exec, g->ev1_node, slot->ev1));
       if (g->evr_node) CUDA_TRY(cudaGraphExecEventRecordNodeSetEvent(g->exec, g->evr_node, slot->ev_round));
@@ -785,6 +817,22 @@ static void reset_totals(casa_handle* h) {
 
 static int collect(casa_handle* h) {
   int first_rc = CASA_OK;
+  for (int i = 0; i < kMaxLanes; ++i) {  // lanes: their calls are this handle's calls
+    casa_handle* s = h->lane[i];
+    if (!s) continue;
+    const int rc = collect(s);
+    if (first_rc == CASA_OK) first_rc = rc;
+    h->score_ms += s->score_ms;
+    h->score_launches += s->score_launches;
+    h->rounds_total += s->rounds_total;
+    h->launches_total += s->launches_total;
+    for (int k = 0; k < 4; ++k) h->stats[k] += s->stats[k];
+    if (i == h->lane_last) {
+      h->last_status = s->last_status;
+      h->last_launches = s->last_launches;
+    }
+    reset_totals(s);
+  }
   while (h->slot_tail < h->slot_head) {
     CallSlot& c = h->slots[h->slot_tail % kCallSlots];
     CUDA_TRY(cudaEventSynchronize(c.ev_round));
@@ -816,6 +864,31 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
                             const casa_ransac_debug* debug, void* stream) {
   if (!h) return fail(CASA_ERR_INVALID, "handle is NULL");
   if (!mask || !vertex || !out_points) return fail(CASA_ERR_INVALID, "mask / vertex / out_points must not be NULL");
+  if (h->async_mode >= 2 && !debug && !h->is_lane) {  // lanes: this vote runs on a sub-handle's own stream
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int k = h->lane_next % h->async_mode;
+    if (!h->lane[k]) {
+      int rcl = casa_create(h->device, &h->lane[k]);
+      if (rcl) return rcl;
+      h->lane[k]->is_lane = 1;
+      h->lane[k]->async_mode = 1;
+      CUDA_TRY(cudaEventCreateWithFlags(&h->lane_fork[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->lane_done[k], cudaEventDisableTiming));
+    }
+    casa_handle* sub = h->lane[k];
+    sub->timing = h->timing;
+    sub->vertex_mapped = h->vertex_mapped;
+    sub->host_not_binary = h->host_not_binary;
+    CUDA_TRY(cudaEventRecord(h->lane_fork[k], (cudaStream_t)stream));  // the lane sees what the caller queued so far
+    CUDA_TRY(cudaStreamWaitEvent(sub->own_stream, h->lane_fork[k], 0));
+    const int rcl = ransac_vote_impl(sub, p, mask, mask_is_seg, vertex, idxs, selection, out_points, nullptr, (void*)sub->own_stream);
+    CUDA_TRY(cudaEventRecord(h->lane_done[k], sub->own_stream));
+    h->lane_pending[k] = 1;
+    h->lane_last = k;
+    h->lane_next = (k + 1) % h->async_mode;
+    h->last_stream = (cudaStream_t)stream;
+    return rcl;
+  }
   Layout L;
   int rc = make_layout(p, L);
   if (rc) return rc;
@@ -877,13 +950,19 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     steps.push_back(kstep((const void*)k_seg_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d));
   else
     steps.push_back(kstep((const void*)k_mask_bits, dim3(d.nct, d.b), 256).arg(mask).arg(ws).arg(d).arg(vec4));
-  steps.push_back(kstep((const void*)k_job_tables, d.b, 256).arg(ws).arg(d));
-  steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
-  if ((float)d.hw > p->max_num) steps.push_back(kstep((const void*)k_cap_filter, d.J, 1024).arg(ws).arg(d).arg(selection));
-  // round 0's plan only needs the job table: it runs beside the direction gather (side branch, joined by k_hypgen)
-  steps.push_back(kstep((const void*)k_plan, 1, plan_threads).arg(ws).arg(d).arg((int)0).on_side(1));
-  steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gather_gx, d.J), 256)
-                      .arg(vertex).arg(ws).arg(d));
+  // k_place gathers the directions while it scatters the pixels, unless the field lives in mapped host memory (the
+  // host entry point: k_gather_dirs reads full lines over PCIe) or is not 8-byte aligned; jobs above max_num are
+  // gathered after the cap filter
+  const int fuse_gather = (!h->vertex_mapped && (((uintptr_t)vertex) & 7) == 0 && !getenv("CASA_NO_FUSED_GATHER")) ? 1 : 0;
+  const bool may_cap = (float)d.hw > p->max_num;
+  steps.push_back(kstep(d.vn == 9 ? (const void*)k_place<9> : (const void*)k_place<0>, dim3((d.nct + kPlaceSub - 1) / kPlaceSub, d.b), 256).arg(vertex).arg(ws).arg(d).arg(fuse_gather));
+  if (may_cap) steps.push_back(kstep((const void*)k_cap_filter, d.J, 1024).arg(ws).arg(d).arg(selection));
+  // round 0's plan (work items, refinement tiles) only needs the job table: it runs beside the direction gather and
+  // k_hypgen (side branch in slot 1, joined by k_score)
+  steps.push_back(kstep((const void*)k_plan, 1, plan_threads).arg(ws).arg(d).arg((int)0).on_side(1, 1));
+  if (!fuse_gather || may_cap)
+    steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gather_gx, d.J), 256)
+                        .arg(vertex).arg(ws).arg(d).arg(fuse_gather));
   for (int part = 0; part < 2; ++part) {  // part 0: round 0; part 1: the WHILE body (rnd = -1: read ctrl[CTRL_ROUND])
     const int rnd = part == 0 ? 0 : -1;
     if (part == 1) {
@@ -893,11 +972,14 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     }
     const size_t n0 = steps.size();
     Step hg = kstep((const void*)k_hypgen, dim3((d.hn * d.vn + 255) / 256, d.J), 256).arg(ws).arg(d).arg(fc).arg(idxs).arg(rnd).arg(dbg.hyps);
-    if (part == 0) hg.joins();
     steps.push_back(hg);
     // the timing events hang off the chain as leaves: ev0 fires when k_hypgen is done, ev1 when k_score is done
     if (part == 0 && h->timing) steps.push_back(special(STEP_EV0, 1));
-    steps.push_back(kstep(score_fn, h->sm_count * h->score_occ, kScoreThreads).arg(sa));
+    {
+      Step sc = kstep(score_fn, h->sm_count * h->score_occ, kScoreThreads).arg(sa);
+      if (part == 0) sc.joins(1);
+      steps.push_back(sc);
+    }
     if (part == 0 && h->timing) steps.push_back(special(STEP_EV1, 1));
     steps.push_back(kstep((const void*)k_update, d.J, 32 * d.vn).arg(ws).arg(d).arg(rnd).arg(dbg).cond().arg(h->sticky));
     if (part == 1) {
@@ -1052,6 +1134,7 @@ extern "C" int casa_ransac_vote_dlpack(casa_handle* h, const casa_ransac_params*
   rc = ransac_vote_impl(h, &q, dl_data(m), mask_is_seg, dl_data(v), nullptr, nullptr, (float*)dl_data(o), nullptr, stream);
   // the capsules are consumed either way: their deleters run once the work queued so far on `stream` has finished
   cudaEvent_t done = nullptr;
+  if (h->async_mode >= 2 && h->lane_last >= 0) stream = (void*)h->lane[h->lane_last]->own_stream;  // the vote ran on a lane
   if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess && cudaEventRecord(done, (cudaStream_t)stream) == cudaSuccess) {
     deferred(h).push_back({m, done});
     deferred(h).push_back({v, done});
@@ -1096,6 +1179,11 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     explicit AsyncOff(casa_handle* hh) : h(hh), saved(hh->async_mode) { h->async_mode = 0; }
     ~AsyncOff() { h->async_mode = saved; }
   } async_off(h);
+  struct MappedFlag {  // set while the vote reads the vector field from mapped host memory (k_gather_dirs, not k_place)
+    casa_handle* h;
+    explicit MappedFlag(casa_handle* hh) : h(hh) {}
+    ~MappedFlag() { h->vertex_mapped = 0; }
+  } mapped_flag(h);
   // Pinned (page-locked) host buffers: the mask is DMA-copied in up to 4 image ranges on a copy stream while the
   // previous range is being voted on, and the vector field is never copied — k_gather_dirs reads only the masked
   // pixels' rows straight from the mapped host buffer.  About 200 MB instead of 511 MB cross PCIe for a 16-frame
@@ -1121,6 +1209,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     rc = casa_ransac_vote(h, p, dmask, dvert, nullptr, nullptr, dout, nullptr, (void*)st);
     if (rc) return rc;
   } else {
+    h->vertex_mapped = 1;
     int parts = p->b >= 8 ? 4 : (p->b >= 2 ? 2 : 1);
     if (getenv("CASA_HOST_PARTS")) parts = atoi(getenv("CASA_HOST_PARTS"));
     if (parts < 1) parts = 1;
@@ -1308,8 +1397,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
     if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_ls_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     steps.push_back(kstep((const void*)k_ls_classify, dim3(d.nct, d.b), 256, sm).arg(seg).arg(ws).arg(d).arg(lw).arg(ld));
   }
-  steps.push_back(kstep((const void*)k_job_tables, d.b, 256).arg(ws).arg(d));
-  steps.push_back(kstep((const void*)k_scatter, dim3(d.nct, d.b), 256).arg(ws).arg(d));
+  steps.push_back(kstep((const void*)k_place<0>, dim3((d.nct + kPlaceSub - 1) / kPlaceSub, d.b), 256).arg((const float*)nullptr).arg(ws).arg(d).arg((int)0));
   // topology: the work-item / tile plan only needs the job table and runs beside the component chain (side branch)
   steps.push_back(kstep((const void*)k_plan, 1, d.J > 256 ? 1024 : 256).arg(ws).arg(d).arg((int)0).on_side(1));
   const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
@@ -1323,7 +1411,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   if (grad) {
     // the backward pass reads the gathered directions / weights / confidences: the three-kernel form fills them
     steps.push_back(kstep(d.vn == 9 ? (const void*)k_gather_dirs<18> : (const void*)k_gather_dirs<0>, dim3(gx, d.J), 256)
-                        .arg(direct).arg(ws).arg(d).joins());
+                        .arg(direct).arg(ws).arg(d).arg((int)0).joins());
     steps.push_back(kstep((const void*)k_ls_weights, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(conf));
     steps.push_back(kstep((const void*)k_ls_reduce, dim3(grid_x, d.vn), 256).arg(ws).arg(d).arg(lw).arg(ld));
   } else {
@@ -1441,7 +1529,32 @@ extern "C" int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t ma
 
 extern "C" int casa_set_async(casa_handle* h, int enable) {
   if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
-  h->async_mode = enable ? 1 : 0;
+  if (enable < 0 || enable > kMaxLanes)
+    return fail(CASA_ERR_INVALID, "casa_set_async: mode %d (0 synchronous, 1 asynchronous, 2..%d asynchronous on that many lanes)", enable, kMaxLanes);
+  if (h->async_mode >= 2 && enable != h->async_mode) {  // leaving a lane mode: everything the lanes hold has run when this returns
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < kMaxLanes; ++i)
+      if (h->lane[i] && h->lane_pending[i]) {
+        CUDA_TRY(cudaStreamSynchronize(h->lane[i]->own_stream));
+        h->lane_pending[i] = 0;
+      }
+  }
+  if (h->async_mode == 0 && enable != 0) {  // an asynchronous session starts clean: synchronous calls reported their own status
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->last_stream) CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+    CUDA_TRY(cudaMemset(h->sticky, 0, sizeof(uint32_t)));
+  }
+  h->async_mode = enable;
+  return CASA_OK;
+}
+
+// Orders the outputs of every vote issued in the two-lane mode on `stream` (the caller's stream does not wait for the
+// lanes by itself); a no-op in the other modes, where a vote runs on the caller's stream.
+extern "C" int casa_join(casa_handle* h, void* stream) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int i = 0; i < kMaxLanes; ++i)
+    if (h->lane[i] && h->lane_pending[i]) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->lane_done[i], 0));
   return CASA_OK;
 }
 
@@ -1452,8 +1565,17 @@ extern "C" int casa_sync(casa_handle* h) {
   CUDA_TRY(cudaStreamSynchronize(h->last_stream));
   if (h->deferred_list) run_deferred(h, true);
   CUDA_TRY(cudaMemcpy(h->pinned_sticky, h->sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  const uint32_t st = *h->pinned_sticky;
+  uint32_t st = *h->pinned_sticky;
   if (st) CUDA_TRY(cudaMemset(h->sticky, 0, sizeof(uint32_t)));
+  for (int i = 0; i < kMaxLanes; ++i) {  // lanes: wait for their streams, fold their sticky status words in
+    casa_handle* s = h->lane[i];
+    if (!s) continue;
+    CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    h->lane_pending[i] = 0;
+    CUDA_TRY(cudaMemcpy(s->pinned_sticky, s->sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (*s->pinned_sticky) CUDA_TRY(cudaMemset(s->sticky, 0, sizeof(uint32_t)));
+    st |= *s->pinned_sticky;
+  }
   if (rc) return rc;
   if (st & CASA_STATUS_PIX_OVERFLOW)
     return fail(CASA_ERR_WORKSPACE, "a call since the last casa_sync overflowed its pixel lists (mask not one-hot?); retry with a larger pix_capacity");
@@ -1560,18 +1682,19 @@ extern "C" int casa_allgather_points(casa_handle* h, void* nccl_comm, const floa
 extern "C" int casa_allgather_points_overlapped(casa_handle* h, const float* local, float* gathered, int64_t floats_per_rank,
                                                 void* after_stream, int slot) {
   if (!h || !local || !gathered) return fail(CASA_ERR_INVALID, "NULL argument");
-  if (slot < 0 || slot >= 4) return fail(CASA_ERR_INVALID, "slot %d outside 0..3", slot);
+  if (slot < 0 || slot >= 8) return fail(CASA_ERR_INVALID, "slot %d outside 0..7", slot);
   if (!h->comm) return fail(CASA_ERR_INVALID, "no communicator: call casa_comm_init / casa_comm_attach first");
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->gather_stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->gather_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       CUDA_TRY(cudaEventCreateWithFlags(&h->gather_after[i], cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&h->gather_done[i], cudaEventDisableTiming));
     }
   }
   // the gather stream waits only for what is queued on `after_stream` right now (the vote that produced `local`), so the
   // exchange of step i overlaps the voting of step i + 1 and no compute stream ever waits for a peer
+  if (h->async_mode >= 2 && h->lane_last >= 0) after_stream = (void*)h->lane[h->lane_last]->own_stream;  // the vote ran there
   CUDA_TRY(cudaEventRecord(h->gather_after[slot], (cudaStream_t)after_stream));
   CUDA_TRY(cudaStreamWaitEvent(h->gather_stream, h->gather_after[slot], 0));
   NCCL_TRY(g_nccl.AllGather(local, gathered, (size_t)floats_per_rank, 7, h->comm, h->gather_stream));
@@ -1581,7 +1704,7 @@ extern "C" int casa_allgather_points_overlapped(casa_handle* h, const float* loc
 
 extern "C" int casa_gather_wait(casa_handle* h, int slot, void* stream) {
   if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
-  if (slot < 0 || slot >= 4 || !h->gather_done[slot]) return fail(CASA_ERR_INVALID, "slot %d has no gather in flight", slot);
+  if (slot < 0 || slot >= 8 || !h->gather_done[slot]) return fail(CASA_ERR_INVALID, "slot %d has no gather in flight", slot);
   CUDA_TRY(cudaSetDevice(h->device));
   if (stream == (void*)-1)
     CUDA_TRY(cudaEventSynchronize(h->gather_done[slot]));                       // host wait

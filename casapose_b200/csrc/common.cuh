@@ -10,7 +10,10 @@ namespace casa {
 constexpr int kCountTile = 1024;   // pixels per block in the mask / scatter kernels (256 thr x 4)
 constexpr int kScoreWarps = 8;     // warps per scoring block
 constexpr int kScoreThreads = kScoreWarps * 32;
-constexpr int kChunk = 128;        // pixels per scoring work item (one warp)
+#ifndef CASA_CHUNK
+#define CASA_CHUNK 128
+#endif
+constexpr int kChunk = CASA_CHUNK;  // pixels per scoring work item (one warp); 256 is an A/B build (profiles/r02_ab.txt)
 constexpr int kRefineTile = 1024;  // pixels per reduction tile of the LS layer (256 threads x 4)
 constexpr int kVoteTile = 2048;    // pixels per refinement tile of the voting path (256 threads x 8)
 
@@ -48,7 +51,6 @@ struct FilterConsts {
 struct WS {
   uint32_t* bits;      // [b*h*w]        class-membership bit mask per pixel
   int* tile_cnt;       // [b][oc][nct]   per count-tile class counts
-  int* tile_base;      // [b][oc][nct]   exclusive prefix of tile_cnt
   uint32_t* pix;       // [b][cap]       compacted pixel lists, (y<<16|x), raster order per class
   float2* vdir;        // [b][cap*vn]    compacted directions (dy,dx): job j, keypoint v, pixel t at
                        //                (img*cap + job_off[j])*vn + v*tn[j] + t  — gathered once per call

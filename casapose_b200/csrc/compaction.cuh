@@ -5,13 +5,13 @@
 // pairs of the batch at once:
 //   k_mask_bits   reads the float mask ONCE (the only pass over [b,h,w,oc]), writes one
 //                 class-membership word per pixel and per-tile class counts (warp ballots);
-//   k_job_tables  exclusive prefix over the tiles of each (image, class); class offsets, foreground_num gate (:290),
-//                 down-sampling threshold (:298);
-//   k_scatter     raster-order scatter of packed pixel coordinates (y<<16 | x) — the order is
-//                 semantically required because hypothesis indices address this list (:216);
-//   k_cap_filter  in-place ordered filter  selection < max_num / foreground_num  (:295-301).
-// The vector field is NOT copied: the scoring kernels gather (dy,dx) straight from `vertex`
-// through the pixel list, so only masked pixels of the 18-channel field are ever read.
+//   k_place       job table (class offsets, foreground_num gate :290, down-sampling threshold :298), raster-order
+//                 scatter of packed pixel coordinates (y<<16 | x) — the order is semantically required because
+//                 hypothesis indices address this list (:216) — and the gather of the listed pixels' directions;
+//   k_cap_filter  in-place ordered filter  selection < max_num / foreground_num  (:295-301);
+//   k_gather_dirs direction gather for what k_place did not take: jobs above max_num (after the filter) and vector
+//                 fields in mapped host memory (full-line reads over PCIe).
+// Only masked pixels of the 18-channel field are ever read.
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -166,117 +166,166 @@ __global__ void __launch_bounds__(256) k_seg_bits(const float* __restrict__ seg,
   if (tid < d.oc) ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile] = scnt[tid];
 }
 
-// One block (256 threads) per image.  Warps stride over the image's classes: exclusive prefix of the class's tile
-// counts (tile_base) and foreground_num (:287); then one thread lays out the image's pixel list: class offsets, the
-// foreground_num gate (:290), the down-sampling threshold (:298).
-__global__ void __launch_bounds__(256) k_job_tables(WS ws, Dims d) {
-  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Second (and last) pass of the compaction, one block per (1024-pixel tile, image): job table, raster-order scatter
+// and — for device-resident vector fields — the direction gather, in one kernel (round 1 and the first half of
+// round 2 ran k_job_tables -> k_scatter -> k_gather_dirs: 54 us of launches per 16 frames).
+//   * every block that holds a masked pixel re-derives what it needs from the tile counts of its image (oc x nct
+//     ints, L2-resident): the class totals = foreground_num (:287) and the totals of the tiles in front of it;
+//   * one thread lays out the image's pixel list from the totals: class offsets, the foreground_num gate (:290), the
+//     down-sampling threshold (:298), the overflow rule; the block of tile 0 publishes this job table;
+//   * masked pixels are written in raster order (ballot + prefix popcount) — semantically required, hypothesis
+//     indices address the list (:216) — and, when `gather` is set, the pixel's (dy,dx) row is copied into the
+//     keypoint-major direction buffer at the same list position (direct = boolean_mask(vertex, mask), :308).  Jobs
+//     above max_num are gathered after k_cap_filter (k_gather_dirs, only_capped), gated jobs never.
+constexpr int kPlaceSub = 4;  // count tiles per k_place block (4096 pixels, 16 per thread)
+template <int VN>             // keypoints per row when known at compile time (9), 0 = runtime
+__global__ void __launch_bounds__(256, 4) k_place(const float* __restrict__ vertex, WS ws, Dims d, int gather) {
+  const int img = blockIdx.y, tile0 = blockIdx.x * kPlaceSub;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kSlots = kPlaceSub * 4;  // pixels per thread; slot j covers pixels [j*256, (j+1)*256) of the block
+  __shared__ int wcnt[32][kSlots * 8];   // [class][slot*8 + warp]
+  __shared__ int scnt[32], s_tot[32], s_pre[32], s_off[32], s_flags[32];
+  // every load the block needs is issued up front (one round trip to L2): its pixels' membership words and the
+  // tile counts of its image — warp w scans classes w, w + 8, ...: total, total in front of this block, own count
+  uint32_t m[kSlots];
+  const int p0 = tile0 * kCountTile;
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) {
+    const int p = p0 + j * 256 + tid;
+    m[j] = p < d.hw ? __ldg(ws.bits + (size_t)img * d.hw + p) : 0u;
+  }
   for (int c = warp; c < d.oc; c += 8) {
-    const int job = img * d.oc + c;
-    const int* cnt = ws.tile_cnt + (size_t)job * d.nct;
-    int* base = ws.tile_base + (size_t)job * d.nct;
-    int run = 0;
-    for (int s = 0; s < d.nct; s += 32 * 16) {  // every lane takes 16 consecutive tiles: all loads in flight at once
-      int v[16];
-      const int i0 = s + lane * 16;
+    const int* cnt = ws.tile_cnt + ((size_t)img * d.oc + c) * d.nct;
+    int tot = 0, pre = 0, own = 0;
+    for (int t0 = 0; t0 < d.nct; t0 += 320) {  // ten loads per lane in flight (nct = 300 at 480 x 640)
+      int v[10];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = i0 + k < d.nct ? cnt[i0 + k] : 0;
-      int tot = 0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) tot += v[k];
-      int x = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
+      for (int k = 0; k < 10; ++k) {
+        const int t = t0 + k * 32 + lane;
+        v[k] = t < d.nct ? __ldg(cnt + t) : 0;
       }
-      int acc = run + x - tot;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        if (i0 + k < d.nct) base[i0 + k] = acc;
-        acc += v[k];
+      for (int k = 0; k < 10; ++k) {
+        const int t = t0 + k * 32 + lane;
+        tot += v[k];
+        pre += t < tile0 ? v[k] : 0;
+        own += (t >= tile0 && t < tile0 + kPlaceSub) ? v[k] : 0;
       }
-      run += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (lane == 0) ws.job_tn0[job] = run;
+    tot = __reduce_add_sync(0xffffffffu, tot);
+    pre = __reduce_add_sync(0xffffffffu, pre);
+    own = __reduce_add_sync(0xffffffffu, own);
+    if (lane == 0) {
+      s_tot[c] = tot;
+      s_pre[c] = pre;
+      scnt[c] = own;
+    }
   }
   __syncthreads();
-  if (tid != 0) return;
-  int off = 0;
-  for (int c = 0; c < d.oc; ++c) {
-    const int job = img * d.oc + c;
-    const int tn0 = ws.job_tn0[job];
-    int flags = 0;
-    const float fg = (float)tn0;  // tf.reduce_sum of a {0,1} mask (:287)
-    if (fg < d.min_num) flags |= JOB_GATED;               // :290
-    float thr = 1.f;
-    if (fg > d.max_num) {                                 // :295
-      flags |= JOB_NEEDS_CAP;
-      thr = __fdiv_rn(d.max_num, fg);                     // :298
+  const int mine = tid < d.oc ? scnt[tid] : 0;
+  if (__syncthreads_or(mine) == 0 && tile0 != 0) return;  // pure background: nothing to place
+  if (tid == 0) {
+    int off = 0;
+    for (int c = 0; c < d.oc; ++c) {
+      const int job = img * d.oc + c;
+      const int tn0 = s_tot[c];
+      int flags = 0;
+      const float fg = (float)tn0;  // tf.reduce_sum of a {0,1} mask (:287)
+      if (fg < d.min_num) flags |= JOB_GATED;               // :290
+      float thr = 1.f;
+      if (fg > d.max_num) {                                 // :295
+        flags |= JOB_NEEDS_CAP;
+        thr = __fdiv_rn(d.max_num, fg);                     // :298
+      }
+      if (off + tn0 > d.cap) flags |= JOB_GATED | JOB_OVERFLOW;
+      if (!(flags & JOB_GATED) && tn0 > 0) flags |= JOB_ACTIVE;  // loop state of round 0 (:310-316)
+      s_off[c] = off;
+      s_flags[c] = flags;
+      if (tile0 == 0) {
+        if (flags & JOB_OVERFLOW) atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_PIX_OVERFLOW);
+        ws.job_tn0[job] = tn0;
+        ws.job_tn[job] = (flags & JOB_OVERFLOW) ? 0 : tn0;
+        ws.job_off[job] = off;
+        ws.job_flags[job] = flags;
+        ws.job_rounds[job] = 0;
+        ws.job_done[job] = 0;
+        ws.job_selthr[job] = thr;
+      }
+      if (!(flags & JOB_OVERFLOW)) off += tn0;
     }
-    if (off + tn0 > d.cap) {
-      flags |= JOB_GATED | JOB_OVERFLOW;
-      atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_PIX_OVERFLOW);
-    }
-    ws.job_tn[job] = (flags & JOB_OVERFLOW) ? 0 : tn0;
-    ws.job_off[job] = off;
-    ws.job_flags[job] = flags;
-    ws.job_rounds[job] = 0;
-    ws.job_done[job] = 0;
-    ws.job_selthr[job] = thr;
-    if (!(flags & JOB_OVERFLOW)) off += tn0;
   }
-}
-
-__global__ void __launch_bounds__(256) k_scatter(WS ws, Dims d) {
-  const int img = blockIdx.y, tile = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int wcnt[32][32];  // [class][slot*8 + warp]
-  __shared__ int scnt[32];      // this tile's class counts
-  int mine = 0;
-  if (tid < d.oc) mine = scnt[tid] = ws.tile_cnt[((size_t)img * d.oc + tid) * d.nct + tile];
-  if (__syncthreads_or(mine) == 0) return;  // most tiles are pure background: nothing to scatter
-  uint32_t m[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int p = tile * kCountTile + k * 256 + tid;
-    m[k] = p < d.hw ? ws.bits[(size_t)img * d.hw + p] : 0u;
+  if (tile0 == 0) {  // best-so-far state of the image's jobs (:310-316); k_hypgen no longer waits for k_plan
+    for (int e = tid; e < d.oc * d.vn; e += 256) {
+      const size_t o = (size_t)img * d.oc * d.vn + e;
+      ws.win_ratio[o] = 0.f;
+      ws.win_pts[o] = make_float2(0.f, 0.f);
+      ws.n_exact[o] = 0;
+    }
   }
   for (int c = 0; c < d.oc; ++c) {
     if (scnt[c] == 0) continue;  // block-uniform
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (m[k] >> c) & 1u);
-      if (lane == 0) wcnt[c][k * 8 + warp] = __popc(bal);
+    for (int j = 0; j < kSlots; ++j) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (m[j] >> c) & 1u);
+      if (lane == 0) wcnt[c][j * 8 + warp] = __popc(bal);
     }
   }
   __syncthreads();
-  for (int c = warp; c < d.oc; c += 8) {
+  for (int c = warp; c < d.oc; c += 8) {  // exclusive prefix over the class's kSlots*8 warp counts, kPlaceSub per lane
     if (scnt[c] == 0) continue;
-    const int v = wcnt[c][lane];
-    int x = v;
+    int v[kPlaceSub], tot = 0;
+#pragma unroll
+    for (int k = 0; k < kPlaceSub; ++k) {
+      v[k] = wcnt[c][lane * kPlaceSub + k];
+      tot += v[k];
+    }
+    int x = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
     }
-    wcnt[c][lane] = x - v;  // exclusive
+    int acc = x - tot;
+#pragma unroll
+    for (int k = 0; k < kPlaceSub; ++k) {
+      wcnt[c][lane * kPlaceSub + k] = acc;
+      acc += v[k];
+    }
   }
   __syncthreads();
+  const int vn = VN ? VN : d.vn;
+  const int vslots = vn * d.vpc;
   for (int c = 0; c < d.oc; ++c) {
     if (scnt[c] == 0) continue;
-    const int job = img * d.oc + c;
-    if (ws.job_flags[job] & JOB_OVERFLOW) continue;
-    const int tbase = ws.tile_base[((size_t)img * d.oc + c) * d.nct + tile];
-    uint32_t* out = ws.pix + (size_t)img * d.cap + ws.job_off[job];
+    const int flags = s_flags[c];
+    if (flags & JOB_OVERFLOW) continue;
+    const int tn = s_tot[c];
+    const int tbase = s_pre[c];
+    uint32_t* out = ws.pix + (size_t)img * d.cap + s_off[c];
+    const bool dirs = gather && !(flags & (JOB_GATED | JOB_NEEDS_CAP));
+    const float2* vfield = reinterpret_cast<const float2*>(vertex) + (size_t)img * d.hw * vslots + (d.vpc > 1 ? c * vn : 0);
+    float2* dst0 = ws.vdir + ((size_t)img * d.cap + s_off[c]) * vn;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool bit = (m[k] >> c) & 1u;
+    for (int j = 0; j < kSlots; ++j) {
+      const bool bit = (m[j] >> c) & 1u;
       const unsigned bal = __ballot_sync(0xffffffffu, bit);
       if (bit) {
-        const int p = tile * kCountTile + k * 256 + tid;
+        const int p = p0 + j * 256 + tid;
         const int y = p / d.w, x = p - y * d.w;
-        out[tbase + wcnt[c][k * 8 + warp] + __popc(bal & lanemask_lt())] = ((uint32_t)y << 16) | (uint32_t)x;
+        const int slot = tbase + wcnt[c][j * 8 + warp] + __popc(bal & lanemask_lt());
+        out[slot] = ((uint32_t)y << 16) | (uint32_t)x;
+        if (dirs) {
+          const float2* row = vfield + (size_t)p * vslots;
+          if (VN) {
+            float2 r[VN ? VN : 1];
+#pragma unroll
+            for (int v = 0; v < VN; ++v) r[v] = __ldg(row + v);
+#pragma unroll
+            for (int v = 0; v < VN; ++v) dst0[(size_t)v * tn + slot] = r[v];
+          } else {
+            for (int v = 0; v < vn; ++v) dst0[(size_t)v * tn + slot] = __ldg(row + v);
+          }
+        }
       }
     }
   }
@@ -321,7 +370,10 @@ __global__ void __launch_bounds__(1024) k_cap_filter(WS ws, Dims d, const float*
   }
   if (tid == 0) {
     ws.job_tn[job] = srun;
-    if (srun == 0) atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_EMPTY_AFTER_CAP);
+    if (srun == 0) {
+      ws.job_flags[job] = flags & ~JOB_ACTIVE;  // nothing left to vote on (k_place set the flag from foreground_num)
+      atomicOr(reinterpret_cast<unsigned*>(&ws.ctrl[CTRL_STATUS]), CASA_STATUS_EMPTY_AFTER_CAP);
+    }
   }
 }
 
@@ -331,11 +383,12 @@ __global__ void __launch_bounds__(1024) k_cap_filter(WS ws, Dims d, const float*
 // row is read once (the only access to `vertex`, which may be device memory or mapped pinned host
 // memory — then only masked pixels of the field cross PCIe), the writes are coalesced per keypoint.
 template <int ROWF>  // floats per pixel row when known at compile time (18 for vn = 9), 0 = runtime
-__global__ void __launch_bounds__(256) k_gather_dirs(const float* __restrict__ vertex, WS ws, Dims d) {
+__global__ void __launch_bounds__(256) k_gather_dirs(const float* __restrict__ vertex, WS ws, Dims d, int only_capped) {
   const int job = blockIdx.y, img = job / d.oc, cls = job - img * d.oc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tn = ws.job_tn[job];
   if (tn <= 0 || (ws.job_flags[job] & JOB_GATED)) return;
+  if (only_capped && !(ws.job_flags[job] & JOB_NEEDS_CAP)) return;  // the others were gathered by k_place
   const int vslots = d.vn * d.vpc;
   const int rowf = ROWF ? ROWF : 2 * d.vn;  // floats fetched per pixel (<= 32)
   const float* vfield = vertex + (size_t)img * d.hw * vslots * 2 + (d.vpc > 1 ? cls * d.vn * 2 : 0);

@@ -94,17 +94,8 @@ __global__ void __launch_bounds__(1024) k_plan(WS ws, Dims d, int rnd) {
     const int job = s + tid;
     int ci = 0, cr = 0;
     if (job < d.J) {
-      int flags = ws.job_flags[job];
+      const int flags = ws.job_flags[job];  // JOB_ACTIVE and the best-so-far state of round 0 come from k_place
       const int tn = ws.job_tn[job];
-      if (rnd == 0) {  // loop state (:310-316)
-        flags = (!(flags & JOB_GATED) && tn > 0) ? (flags | JOB_ACTIVE) : (flags & ~JOB_ACTIVE);
-        ws.job_flags[job] = flags;
-        for (int v = 0; v < d.vn; ++v) {
-          ws.win_ratio[job * d.vn + v] = 0.f;
-          ws.win_pts[job * d.vn + v] = make_float2(0.f, 0.f);
-          ws.n_exact[job * d.vn + v] = 0;
-        }
-      }
       if (flags & JOB_ACTIVE) ci = ((tn + kChunk - 1) / kChunk) * d.vn;
       if (!(flags & JOB_GATED) && tn > 0) cr = (tn + d.rtile - 1) / d.rtile;
     }

@@ -239,9 +239,18 @@ int casa_pose_errors(casa_handle* h, int32_t n, int32_t m, int32_t maxp, const f
  *     queue back to back on the GPU (the data-parallel serving loop).  casa_sync(h) waits for every call issued on
  *     the handle (including refinement / solve) and returns the first error any of them raised; at most 256 calls
  *     may be outstanding before the library collects the oldest ones itself.
+ *   asynchronous on n lanes (casa_set_async(h, n), n = 2..4): as above, and consecutive votes rotate over n internal
+ *     lanes (own workspace, own stream, forked from `stream` by an event at call time), so that the compaction and
+ *     hypothesis kernels and the refinements of n votes overlap — they are latency-bound — while the scoring kernels run
+ *     back to back, each filling the GPU alone.  The inputs of a vote must stay untouched and its output is NOT ordered
+ *     on `stream` until casa_join(h, stream) (device-side: `stream` waits for the lanes) or casa_sync(h) (host-side).
+ *     casa_allgather_points_overlapped follows the lane of the last vote by itself.  casa_get_timing's k_score event
+ *     pairs include the time a launch waits behind the previous lane's k_score: time the kernel in mode 0 / 1.  Debug
+ *     calls, the host-buffer entry point and the LS layer always run on the caller's stream.
  */
-int casa_set_async(casa_handle* h, int enable);
+int casa_set_async(casa_handle* h, int mode);
 int casa_sync(casa_handle* h);
+int casa_join(casa_handle* h, void* stream);
 
 /*
  * DLPack entry point: the same vote with the tensors handed over as DLManagedTensor* (the pointer inside a "dltensor"
@@ -268,7 +277,7 @@ int casa_ransac_vote_dlpack(casa_handle* h, const casa_ransac_params* p, void* m
  *   casa_allgather_points ncclAllGather of `floats_per_rank` float32 per rank on `stream` (nccl_comm NULL: the handle's)
  *   casa_allgather_points_overlapped  the same on the handle's own gather stream, ordered only behind what is queued
  *                         on `after_stream` at the time of the call: the exchange of step i overlaps the voting of
- *                         step i+1 and no compute stream ever waits for a peer; `slot` (0..3) names the completion
+ *                         step i+1 and no compute stream ever waits for a peer; `slot` (0..7) names the completion
  *                         event, casa_gather_wait(h, slot, stream) makes `stream` wait for it ((void*)-1: the host).
  * NCCL is resolved with dlopen("libnccl.so.2") at the first call (CASA_NCCL_LIB overrides), so the library loads without it.
  */

@@ -248,3 +248,32 @@ def test_host_entry_packs_a_pageable_mask_beside_a_pinned_vertex_field(vote):
     assert torch.equal(dev.cpu(), host)
     again = ransac_voting_layer_all_masks_host(torch.from_numpy(mask), torch.from_numpy(vertex).pin_memory(), 64, seed=9)
     assert torch.equal(host, again)
+
+
+@pytest.mark.parametrize("variant", ["easy", "hard"])
+def test_two_lane_mode_equals_the_synchronous_calls(vote, variant):
+    """casa_set_async(h, 2): consecutive votes alternate between two lanes (own workspace, own stream) and overlap;
+    after casa_join the outputs are those of the synchronous calls, bit for bit (multi-round frames included), and
+    casa_sync reports no error."""
+    from casapose_b200 import _lib
+
+    d = synthetic.make_frames(2, 96, 128, synthetic.CONFIG_8_IDS, variant=variant)
+    mask, vertex = torch.from_numpy(d["mask"]).cuda(), torch.from_numpy(d["vertex"]).cuda()
+    seeds = [3, 4, 5, 6, 7]
+    expect = [vote(mask, vertex, 64, seed=s).clone() for s in seeds]
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.set_async(0, 2, stream)
+    try:
+        outs = [torch.full_like(expect[0], -1.0) for _ in seeds]
+        for s, o in zip(seeds, outs):
+            vote(mask, vertex, 64, seed=s, out=o)
+        _lib.join(0, stream)
+        got = [o.clone() for o in outs]  # on the caller's stream, behind the join
+        _lib.sync(0, stream)
+    finally:
+        _lib.set_async(0, 0, stream)
+    for e, g in zip(expect, got):
+        assert torch.equal(e, g)
+    again = vote(mask, vertex, 64, seed=seeds[0])
+    assert torch.equal(again, expect[0])

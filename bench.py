@@ -180,19 +180,36 @@ def run_ls(args):
     direct = torch.from_numpy(d["vertex"].reshape(B, H, W, 18)).cuda()
     conf = torch.from_numpy(d["conf_logits"]).cuda()
     layer = CoordLSVotingWeighted("ls", OC + 1, num_points=VN, filter_estimates=True)
-    for _ in range(max(args.warmup, 3)):
-        layer([seg, direct, conf], check_finite=False)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lanes = max(1, min(4, args.lanes))
     sampler = ClockSampler(0)
     sampler.start()
-    e0.record()
-    for _ in range(args.steps):
-        out = layer([seg, direct, conf], check_finite=False)
-    e1.record()
-    torch.cuda.synchronize()
+
+    def timed(mode):
+        # mode >= 2: that many calls in flight (casa_set_async: consecutive calls rotate over workspaces / streams, so the
+        # latency-bound classify / place / component kernels of neighbouring calls overlap); 1: one call at a time
+        _lib.set_async(0, mode)
+        for _ in range(max(args.warmup, 3)):
+            layer([seg, direct, conf], check_finite=False)
+        _lib.join(0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if mode == (lanes if lanes >= 2 else 1):
+            sampler.mark()
+        e0.record()
+        for _ in range(args.steps):
+            layer([seg, direct, conf], check_finite=False)
+        _lib.join(0)
+        e1.record()
+        torch.cuda.synchronize()
+        _lib.sync(0)
+        return e0.elapsed_time(e1) / args.steps
+
+    ms = timed(lanes if lanes >= 2 else 1)
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms_one = timed(1) if lanes >= 2 else ms
+    _lib.set_async(0, 0)
+    layer([seg, direct, conf], check_finite=False)
+    torch.cuda.synchronize()
     nl = C.c_int64()
     _lib.check(_lib.lib().casa_last_launches(_lib.handle(0), C.byref(nl)))
     fwd_launches = int(nl.value)
@@ -224,7 +241,8 @@ def run_ls(args):
         "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 elementwise, f64 accumulation",
         "data": "synthetic", "config": {"workload": "config 1 shape: [b,480,640,9+18+9] network-output split -> CoordLSVotingWeighted(filter_estimates=True), batch %d" % B,
-                                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (alg_bytes / 1e6)},
+                                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (alg_bytes / 1e6),
+                                        "calls_in_flight": lanes, "ms_per_step_one_lane": ms_one},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "CoordLSVotingWeighted (k_ls_classify .. k_ls_solve, %d launches replayed as one CUDA graph)" % fwd_launches, "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src},

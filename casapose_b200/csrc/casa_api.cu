@@ -208,6 +208,7 @@ struct casa_handle {
   int64_t rounds_total = 0, launches_total = 0;
   unsigned long long* pinned_stats = nullptr;  // 4 words, page-locked
   int score_occ = 0;
+  int fused_occ = 0;              // resident k_ls_fused blocks per SM (persistent grid of the LS forward call)
   int use_graph = 1;
   // keypoint all-gather (NCCL, resolved with dlopen: the library itself does not link against it)
   void* comm = nullptr;           // ncclComm_t
@@ -413,7 +414,7 @@ size_t bump(size_t& cur, size_t bytes) {
 }
 
 
-int make_layout(const casa_ransac_params* p, Layout& L) {
+int make_layout(const casa_ransac_params* p, Layout& L, int ls_tile = kRefineTile) {
   if (!p) return fail(CASA_ERR_INVALID, "params is NULL");
   if (p->b < 1 || p->h < 1 || p->w < 1 || p->h > 65535 || p->w > 65535)
     return fail(CASA_ERR_INVALID, "bad shape b=%d h=%d w=%d", p->b, p->h, p->w);
@@ -431,7 +432,7 @@ int make_layout(const casa_ransac_params* p, Layout& L) {
   d.J = p->b * p->oc;
   d.nct = (d.hw + kCountTile - 1) / kCountTile;
   d.cap = p->pix_capacity > 0 ? p->pix_capacity : d.hw;
-  const long long rtiles = (long long)d.b * ((long long)d.cap / kRefineTile + d.oc + 1);
+  const long long rtiles = (long long)d.b * ((long long)d.cap / ls_tile + d.oc + 1);  // ls_tile <= kVoteTile: covers the voting path too
   if (rtiles > (1ll << 30) || (long long)d.b * ((long long)d.cap / kChunk + d.oc + 1) * d.vn > (1ll << 30))
     return fail(CASA_ERR_INVALID, "too many work items");
   d.max_rtiles = (int)rtiles;
@@ -859,35 +860,52 @@ static int collect(casa_handle* h) {
   return first_rc;
 }
 
+// Lanes (casa_set_async(h, n >= 2)): the next call runs on sub-handle `lane_next`, on that lane's own stream, behind an
+// event recorded on the caller's stream now (the lane sees what the caller queued so far).
+static int lane_begin(casa_handle* h, void* stream, casa_handle** sub_out, int* k_out) {
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int k = h->lane_next % h->async_mode;
+  if (!h->lane[k]) {
+    int rcl = casa_create(h->device, &h->lane[k]);
+    if (rcl) return rcl;
+    h->lane[k]->is_lane = 1;
+    h->lane[k]->async_mode = 1;
+    CUDA_TRY(cudaEventCreateWithFlags(&h->lane_fork[k], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->lane_done[k], cudaEventDisableTiming));
+  }
+  casa_handle* sub = h->lane[k];
+  sub->timing = h->timing;
+  sub->vertex_mapped = h->vertex_mapped;
+  sub->host_not_binary = h->host_not_binary;
+  CUDA_TRY(cudaEventRecord(h->lane_fork[k], (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(sub->own_stream, h->lane_fork[k], 0));
+  *sub_out = sub;
+  *k_out = k;
+  return CASA_OK;
+}
+
+static int lane_end(casa_handle* h, int k, void* stream) {
+  CUDA_TRY(cudaEventRecord(h->lane_done[k], h->lane[k]->own_stream));
+  h->lane_pending[k] = 1;
+  h->lane_last = k;
+  h->lane_next = (k + 1) % h->async_mode;
+  h->last_stream = (cudaStream_t)stream;
+  return CASA_OK;
+}
+
 static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const float* mask, int mask_is_seg,
                             const float* vertex, const int32_t* idxs, const float* selection, float* out_points,
                             const casa_ransac_debug* debug, void* stream) {
   if (!h) return fail(CASA_ERR_INVALID, "handle is NULL");
   if (!mask || !vertex || !out_points) return fail(CASA_ERR_INVALID, "mask / vertex / out_points must not be NULL");
   if (h->async_mode >= 2 && !debug && !h->is_lane) {  // lanes: this vote runs on a sub-handle's own stream
-    CUDA_TRY(cudaSetDevice(h->device));
-    const int k = h->lane_next % h->async_mode;
-    if (!h->lane[k]) {
-      int rcl = casa_create(h->device, &h->lane[k]);
-      if (rcl) return rcl;
-      h->lane[k]->is_lane = 1;
-      h->lane[k]->async_mode = 1;
-      CUDA_TRY(cudaEventCreateWithFlags(&h->lane_fork[k], cudaEventDisableTiming));
-      CUDA_TRY(cudaEventCreateWithFlags(&h->lane_done[k], cudaEventDisableTiming));
-    }
-    casa_handle* sub = h->lane[k];
-    sub->timing = h->timing;
-    sub->vertex_mapped = h->vertex_mapped;
-    sub->host_not_binary = h->host_not_binary;
-    CUDA_TRY(cudaEventRecord(h->lane_fork[k], (cudaStream_t)stream));  // the lane sees what the caller queued so far
-    CUDA_TRY(cudaStreamWaitEvent(sub->own_stream, h->lane_fork[k], 0));
-    const int rcl = ransac_vote_impl(sub, p, mask, mask_is_seg, vertex, idxs, selection, out_points, nullptr, (void*)sub->own_stream);
-    CUDA_TRY(cudaEventRecord(h->lane_done[k], sub->own_stream));
-    h->lane_pending[k] = 1;
-    h->lane_last = k;
-    h->lane_next = (k + 1) % h->async_mode;
-    h->last_stream = (cudaStream_t)stream;
-    return rcl;
+    casa_handle* sub = nullptr;
+    int k = 0;
+    int rcl = lane_begin(h, stream, &sub, &k);
+    if (rcl) return rcl;
+    rcl = ransac_vote_impl(sub, p, mask, mask_is_seg, vertex, idxs, selection, out_points, nullptr, (void*)sub->own_stream);
+    const int rce = lane_end(h, k, stream);
+    return rcl ? rcl : rce;
   }
   Layout L;
   int rc = make_layout(p, L);
@@ -1319,6 +1337,16 @@ extern "C" int casa_ls_vote(casa_handle* h, const casa_ls_params* p, const float
                             const float* conf, float* out_points, const casa_ls_debug* debug, void* stream) {
   if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
   if (!seg || !direct || !conf || !out_points) return fail(CASA_ERR_INVALID, "seg / direct / conf / out_points must not be NULL");
+  if (h->async_mode >= 2 && !debug && !p->check_finite && !h->is_lane) {  // lanes, as for the votes (check_finite waits for the host)
+    casa_handle* sub = nullptr;
+    int k = 0;
+    int rcl = lane_begin(h, stream, &sub, &k);
+    if (rcl) return rcl;
+    rcl = ls_vote_impl(sub, p, seg, direct, conf, out_points, nullptr, (void*)sub->own_stream, nullptr);
+    const int rce = lane_end(h, k, stream);
+    h->last_launches = sub->last_launches;
+    return rcl ? rcl : rce;
+  }
   return ls_vote_impl(h, p, seg, direct, conf, out_points, debug, stream, nullptr);
 }
 
@@ -1348,18 +1376,26 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   // zero-initialised seg head) can list a pixel several times: the per-image list then needs more than h*w slots.
   // The first attempt uses h*w (or the caller's pix_capacity); an overflow is retried below with the measured need.
   rp.pix_capacity = pix_capacity > 0 ? pix_capacity : p->pix_capacity;
+  // The forward call reduces 512-entry tiles in one fused pass and finds the components over horizontal runs
+  // (k_cc_runs); gradient and debug calls keep the pixel-level union-find, whose forest the backward pass and the
+  // debug outputs read.
+  const bool runs_cc = !grad && !debug && !getenv("CASA_LS_PIXEL_CC");
+  const int ls_tile = grad ? kRefineTile : kFusedTile;
   Layout L;
-  int rc = make_layout(&rp, L);
+  int rc = make_layout(&rp, L, ls_tile);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
-  L.d.rtile = kRefineTile;
+  L.d.rtile = ls_tile;
   const Dims& d = L.d;
   const size_t npx = (size_t)d.b * d.hw;
+  const size_t nle = (size_t)d.b * d.cap;  // list entries
   size_t cur = L.total;
   const size_t off_cls9 = bump(cur, npx), off_parent = bump(cur, npx * 4), off_count = bump(cur, npx * 4),
                off_roots = bump(cur, npx * 4), off_nroots = bump(cur, (size_t)d.b * 4), off_sel = bump(cur, (size_t)d.J * 4),
-               off_wt = bump(cur, (size_t)d.b * d.cap * 4), off_cconf = bump(cur, (size_t)d.b * d.cap * d.vn * 4),
-               off_adj = bump(cur, (size_t)d.J * d.vn * 6 * 4), off_tmp_out = bump(cur, (size_t)d.J * d.vn * 2 * 4);
+               off_wt = bump(cur, nle * 4), off_cconf = bump(cur, nle * d.vn * 4),
+               off_adj = bump(cur, (size_t)d.J * d.vn * 6 * 4), off_tmp_out = bump(cur, (size_t)d.J * d.vn * 2 * 4),
+               off_ridx = bump(cur, nle * 4), off_keep = bump(cur, nle), off_run_pk = bump(cur, nle * 4),
+               off_run_x1 = bump(cur, nle * 4), off_run_parent = bump(cur, nle * 4), off_run_cnt = bump(cur, nle * 4);
   rc = ensure(&h->ws_mem, &h->ws_bytes, cur);
   if (rc) return rc;
   h->clean_ctrl = nullptr;  // the LS layer leaves its own loop state in ctrl / stats
@@ -1375,6 +1411,12 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   lw.sel = (int*)(base + off_sel);
   lw.wt = (float*)(base + off_wt);
   lw.cconf = (float*)(base + off_cconf);
+  lw.ridx = (int*)(base + off_ridx);
+  lw.keep = (unsigned char*)(base + off_keep);
+  lw.run_pk = (uint32_t*)(base + off_run_pk);
+  lw.run_x1 = (int*)(base + off_run_x1);
+  lw.run_parent = (int*)(base + off_run_parent);
+  lw.run_cnt = (int*)(base + off_run_cnt);
   LsDims ld;
   ld.b = d.b; ld.h = d.h; ld.w = d.w; ld.nc = p->num_classes; ld.oc = d.oc; ld.vn = d.vn; ld.hw = d.hw;
   ld.sigmoid_weights = p->sigmoid_weights ? 1 : 0;
@@ -1387,21 +1429,23 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
   if (debug) dbg = *debug;
   int64_t launches = 0;
 
-  CUDA_TRY(cudaMemsetAsync(ws.ctrl, 0, CTRL_WORDS * sizeof(int), st));
-  CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 4 * sizeof(unsigned long long), st));
   // the launch list: replayed as a CUDA graph (kernel parameters patched per call) unless debug outputs are asked for
   std::vector<Step> steps;
   steps.reserve(16);
+  steps.push_back(special(STEP_CLEAR));  // ctrl / stats: one memset node in front of the kernels
   {
     const size_t sm = (size_t)kCountTile * ld.nc * 4;
-    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_ls_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    steps.push_back(kstep((const void*)k_ls_classify, dim3(d.nct, d.b), 256, sm).arg(seg).arg(ws).arg(d).arg(lw).arg(ld));
+    const void* classify = ld.nc == 9 ? (const void*)k_ls_classify<9> : (const void*)k_ls_classify<0>;
+    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    steps.push_back(kstep(classify, dim3(d.nct, d.b), 256, sm).arg(seg).arg(ws).arg(d).arg(lw).arg(ld).arg((int)(runs_cc ? 1 : 0)));
   }
   steps.push_back(kstep((const void*)k_place<0>, dim3((d.nct + kPlaceSub - 1) / kPlaceSub, d.b), 256).arg((const float*)nullptr).arg(ws).arg(d).arg((int)0));
   // topology: the work-item / tile plan only needs the job table and runs beside the component chain (side branch)
   steps.push_back(kstep((const void*)k_plan, 1, d.J > 256 ? 1024 : 256).arg(ws).arg(d).arg((int)0).on_side(1));
   const int gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
-  if (ld.filter) {
+  if (ld.filter && runs_cc) {
+    steps.push_back(kstep((const void*)k_cc_runs, d.J, kCcThreads).arg(ws).arg(d).arg(lw).arg(ld));
+  } else if (ld.filter) {
     steps.push_back(kstep((const void*)k_cc_init, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld));
     steps.push_back(kstep((const void*)k_cc_merge, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld));
     steps.push_back(kstep((const void*)k_cc_flatten, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld));
@@ -1415,7 +1459,13 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
     steps.push_back(kstep((const void*)k_ls_weights, dim3(gx, d.J), 256).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(conf));
     steps.push_back(kstep((const void*)k_ls_reduce, dim3(grid_x, d.vn), 256).arg(ws).arg(d).arg(lw).arg(ld));
   } else {
-    steps.push_back(kstep((const void*)k_ls_fused, grid_x, 32 * d.vn).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(direct).arg(conf).joins());
+    if (h->fused_occ == 0) {
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fused_occ, k_ls_fused, 32 * d.vn, 0));
+      if (h->fused_occ < 1) h->fused_occ = 1;
+    }
+    const int fused_gx = d.max_rtiles < h->sm_count * h->fused_occ ? d.max_rtiles : h->sm_count * h->fused_occ;
+    steps.push_back(kstep((const void*)k_ls_fused, fused_gx, 32 * d.vn).arg(ws).arg(d).arg(lw).arg(ld).arg(seg).arg(direct).arg(conf)
+                        .arg((int)(runs_cc ? 1 : 0)).joins());
   }
   if (!out_points) out_points = (float*)(base + off_tmp_out);
   steps.push_back(kstep((const void*)k_ls_solve, d.J, 32).arg(ws).arg(d).arg(ld).arg(out_points).arg(dbg.sums).arg(h->sticky));
@@ -1426,7 +1476,7 @@ int ls_vote_impl(casa_handle* h, const casa_ls_params* p, const float* seg, cons
     steps.push_back(kstep((const void*)k_ls_adjoint, d.J, 32).arg(ws).arg(d).arg(ld).arg(grad->grad_points).arg(adj));
     steps.push_back(kstep((const void*)k_ls_backward, grid_x, 256).arg(ws).arg(d).arg(lw).arg(ld).arg(adj).arg(grad->grad_direct).arg(grad->grad_conf));
   }
-  launches = (int64_t)steps.size();
+  for (const Step& s2 : steps) launches += s2.kind == STEP_KERNEL;
   rc = (h->use_graph && !debug) ? run_graph(h, steps, ws, st) : run_direct(h, steps, ws, st);
   if (rc) return rc;
   CUDA_TRY(cudaGetLastError());

@@ -34,7 +34,18 @@ struct LsWS {
   int* sel;             // [J]     selected component: root pixel, -1 = none, -2 = label 0 (background)
   float* wt;            // [b*cap] weight hot * component mask of every listed pixel (job list order)
   float* cconf;         // [b*cap*vn] softplus / sigmoid confidence weights, keypoint-major per job like WS::vdir
+  // run-based components (k_cc_runs, forward call): per list entry the index of its horizontal run (-1: not in the
+  // class's int mask) and the component mask; run tables in global memory for jobs with more than kCcRuns runs
+  int* ridx;            // [b*cap]
+  unsigned char* keep;  // [b*cap]
+  uint32_t* run_pk;     // [b*cap]  (y << 16 | x0) of the run
+  int* run_x1;          // [b*cap]
+  int* run_parent;      // [b*cap]
+  int* run_cnt;         // [b*cap]
 };
+
+constexpr unsigned char kOneHotFlag = 0x80;  // cls9 bit 7 (forward call only): softmax(1e6 seg) is exactly one-hot
+constexpr unsigned char kClassMask = 0x3F;
 
 // softmax(seg * 1e6) in float32 (:38-41): z = x * 1e6; e = exp(z - max z); e / sum e
 __device__ __forceinline__ void hard_softmax(const float* __restrict__ row, int nc, float* hot) {
@@ -91,20 +102,33 @@ __device__ __forceinline__ float hot_of_row(const float* row, int nc, int cls) {
 
 // same tiling and outputs as k_mask_bits (compaction.cuh), fed by the segmentation logits: the tile's
 // [1024 x nc] floats are staged in shared memory with coalesced loads, then every thread classifies 4 pixels
+// NC: classes when known at compile time (9: fully unrolled rows, all loads of the tile in flight), 0 = runtime.
+// flag_onehot (forward call): cls9 bit 7 marks pixels whose softmax is exactly one-hot, so that the reduction need not
+// read their logits again.
 extern __shared__ __align__(16) float ls_smem[];
-__global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ seg, WS ws, Dims d, LsWS lw, LsDims ld) {
+template <int NC>
+__global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ seg, WS ws, Dims d, LsWS lw, LsDims ld, int flag_onehot) {
   const int img = blockIdx.y, tile = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
+  const int nc = NC ? NC : ld.nc;
   __shared__ int scnt[32];
   if (tid < 32) scnt[tid] = 0;
   const int p0 = tile * kCountTile;
   const int npx = min(kCountTile, d.hw - p0);
-  const float* slab = seg + ((size_t)img * d.hw + p0) * ld.nc;
-  const int nfl = npx * ld.nc;
-  if (((nfl | (int)(((size_t)img * d.hw + p0) * ld.nc)) & 3) == 0 && (reinterpret_cast<uintptr_t>(seg) & 15) == 0) {
+  const float* slab = seg + ((size_t)img * d.hw + p0) * nc;
+  const int nfl = npx * nc;
+  if (((nfl | (int)(((size_t)img * d.hw + p0) * nc)) & 3) == 0 && (reinterpret_cast<uintptr_t>(seg) & 15) == 0) {
     const float4* slab4 = reinterpret_cast<const float4*>(slab);  // 16-byte aligned slab: 128-bit loads
     float4* sm4 = reinterpret_cast<float4*>(ls_smem);
-    for (int i = tid; i < nfl / 4; i += 256) sm4[i] = __ldg(slab4 + i);
+    if (NC && npx == kCountTile) {  // NC float4 per thread, all in flight before the first store
+      float4 v[NC ? NC : 1];
+#pragma unroll
+      for (int u = 0; u < NC; ++u) v[u] = __ldg(slab4 + u * 256 + tid);
+#pragma unroll
+      for (int u = 0; u < NC; ++u) sm4[u * 256 + tid] = v[u];
+    } else {
+      for (int i = tid; i < nfl / 4; i += 256) sm4[i] = __ldg(slab4 + i);
+    }
   } else {
     for (int i = tid; i < nfl; i += 256) ls_smem[i] = __ldg(slab + i);
   }
@@ -114,10 +138,11 @@ __global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ s
     const int q = k * 256 + tid;
     uint32_t m = 0;
     if (q < npx) {
-      const float* row = ls_smem + q * ld.nc;
+      const float* row = ls_smem + q * nc;
       float mx = -3.4e38f, m2 = -3.4e38f;
       int arg = 0;
-      for (int c = 0; c < ld.nc; ++c) {
+#pragma unroll
+      for (int c = 0; c < nc; ++c) {
         const float z = __fmul_rn(row[c], 1.0e6f);
         if (z > mx) {
           m2 = mx;
@@ -131,17 +156,13 @@ __global__ void __launch_bounds__(256) k_ls_classify(const float* __restrict__ s
       if (mx - m2 > 110.f) {  // exactly one-hot
         if (arg > 0) {
           m = 1u << (arg - 1);
-          c9 = arg;
+          c9 = arg | (flag_onehot ? kOneHotFlag : 0);
         }
       } else {
-        float hot[33];
         float sum = 0.f;
-        for (int c = 0; c < ld.nc; ++c) {
-          hot[c] = expf(__fsub_rn(__fmul_rn(row[c], 1.0e6f), mx));
-          sum = __fadd_rn(sum, hot[c]);
-        }
-        for (int c = 1; c < ld.nc; ++c) {
-          const float hv = __fdiv_rn(hot[c], sum);
+        for (int c = 0; c < nc; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(__fmul_rn(row[c], 1.0e6f), mx)));
+        for (int c = 1; c < nc; ++c) {
+          const float hv = __fdiv_rn(expf(__fsub_rn(__fmul_rn(row[c], 1.0e6f), mx)), sum);
           m |= (uint32_t)(hv != 0.f) << (c - 1);
           if ((int)__fadd_rn(hv, 0.1f) == 1) c9 = c;  // :44 (at most one class can reach 0.9)
         }
@@ -280,6 +301,75 @@ __global__ void __launch_bounds__(256) k_cc_flatten(WS ws, Dims d, LsWS lw, LsDi
   }
 }
 
+// Block-level end of the selection (:64-76): merges the per-thread top-3 lists (shuffle tree inside each warp, then
+// thread 0 over the warp results), adds label 0 (every pixel outside the class's int mask), and returns — in thread 0 —
+// the selected label as a root pixel index, -2 for label 0, -1 for a padding label that matches no pixel.
+template <int NWARPS>
+__device__ __forceinline__ int cc_pick(unsigned long long (&top)[3], int npix, int ncomp, const LsDims& ld) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long other[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) other[k] = __shfl_down_sync(0xffffffffu, top[k], o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      unsigned long long key = other[k];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (key > top[j]) {
+          const unsigned long long t = top[j];
+          top[j] = key;
+          key = t;
+        }
+    }
+  }
+  npix = __reduce_add_sync(0xffffffffu, npix);
+  ncomp = __reduce_add_sync(0xffffffffu, ncomp);
+  __shared__ unsigned long long stop[NWARPS * 3];
+  __shared__ int snp[NWARPS], snc[NWARPS];
+  if (lane == 0) {
+    for (int k = 0; k < 3; ++k) stop[warp * 3 + k] = top[k];
+    snp[warp] = npix;
+    snc[warp] = ncomp;
+  }
+  __syncthreads();
+  int sel = -1;                         // padding label: matches no pixel
+  if (tid == 0) {
+    unsigned long long best[3] = {0ull, 0ull, 0ull};
+    int tp = 0, tc = 0;
+    for (int i = 0; i < NWARPS; ++i) {
+      tp += snp[i];
+      tc += snc[i];
+      for (int k = 0; k < 3; ++k) {
+        unsigned long long key = stop[i * 3 + k];
+        if (key == 0ull) continue;
+        for (int j = 0; j < 3; ++j)
+          if (key > best[j]) {
+            const unsigned long long t = best[j];
+            best[j] = key;
+            key = t;
+          }
+      }
+    }
+    const int bg = ld.hw - tp;  // label 0 of this class's int image
+    const unsigned vbg = bg < ld.min_component ? 0u : (unsigned)bg;
+    unsigned long long key = ((unsigned long long)vbg << 32) | 0xFFFFFFFFull;  // label 0: wins every tie
+    for (int j = 0; j < 3; ++j)
+      if (key > best[j]) {
+        const unsigned long long t = best[j];
+        best[j] = key;
+        key = t;
+      }
+    if (ld.which < tc + 1) {            // real entries: label 0 and tc components
+      const unsigned long long k = best[ld.which];
+      const unsigned lab = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+      sel = lab == 0u ? -2 : (int)lab - 1;
+    }
+  }
+  return sel;
+}
+
 // one block per (image, class): bincount -> threshold -> top_k -> pick index `which` (:64-76).
 // Entries are label 0 (every pixel outside the class's int mask) and the components; the component with
 // the smaller root pixel has the smaller tfa label.  key = (value << 32) | ~label : descending order.
@@ -305,68 +395,175 @@ __global__ void __launch_bounds__(256) k_cc_select(LsWS lw, LsDims ld) {
         key = t;
       }
   }
-  // merge the per-thread top-3 lists: shuffle tree inside each warp, then thread 0 over the 8 warp results
-  const int lane = tid & 31, warp = tid >> 5;
+  const int sel = cc_pick<8>(top, npix, ncomp, ld);
+  if (tid == 0) lw.sel[job] = sel;
+}
+
+// ---------------------------------------------------------------------------------- run-based components (forward)
+// The forward call replaces k_cc_init / merge / flatten / select (63 us per 16 frames, global-memory union-find over
+// pixels) by ONE kernel over horizontal runs: a job's raster-ordered pixel list is a sequence of runs (some hundred per
+// object), the 4-connected components of the pixels are the components of the run-adjacency graph (runs of adjacent
+// rows whose x ranges intersect), and a union-find over runs fits shared memory.  One block per job:
+//   1. scan the list: run index of every entry (block-wide prefix of the run starts), run table (y, x0, x1);
+//   2. every run looks up the runs of the row above that overlap it (binary search in the sorted table) and unions;
+//   3. roots (smallest run = smallest pixel index = TFA's label order), component sizes;
+//   4. the reference's selection (cc_pick);  5. the component mask of every list entry.
+// Jobs with more than kCcRuns runs use the same code on run tables in global memory.
+constexpr int kCcThreads = 512;
+constexpr int kCcRuns = 2048;
+constexpr int kCcPer = 4;  // list entries per thread and trip
+
+__global__ void __launch_bounds__(kCcThreads) k_cc_runs(WS ws, Dims d, LsWS lw, LsDims ld) {
+  const int job = blockIdx.x, img = job / d.oc, c = job - img * d.oc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tn = ws.job_tn[job];
+  const size_t lbase = (size_t)img * d.cap + ws.job_off[job];
+  const uint32_t* pix = ws.pix + lbase;
+  const unsigned char* cls = lw.cls9 + (size_t)img * ld.hw;
+  int* ridx = lw.ridx + lbase;
+  unsigned char* keep = lw.keep + lbase;
+  __shared__ uint32_t s_pk[kCcRuns];
+  __shared__ int s_x1[kCcRuns], s_parent[kCcRuns], s_cnt[kCcRuns];
+  __shared__ int s_warp[kCcThreads / 32];
+  __shared__ int s_sel;
+  uint32_t* r_pk = s_pk;
+  int *r_x1 = s_x1, *r_parent = s_parent, *r_cnt = s_cnt;
+  int cap_runs = kCcRuns, nruns = 0;
+  const unsigned char want = (unsigned char)(c + 1);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int run0 = 0;  // runs that start in front of this trip (block-uniform)
+    for (int base = 0; base < tn; base += kCcThreads * kCcPer) {
+      // thread-contiguous entries t0 .. t0 + kCcPer - 1, plus the neighbours on either side
+      const int t0 = base + tid * kCcPer;
+      uint32_t pk[kCcPer + 2];
+      bool fg[kCcPer + 2];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    unsigned long long other[3];
+      for (int k = 0; k < kCcPer + 2; ++k) {
+        const int t = t0 + k - 1;
+        pk[k] = (t >= 0 && t < tn) ? __ldg(pix + t) : 0xFFFFFFFFu;
+      }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) other[k] = __shfl_down_sync(0xffffffffu, top[k], o);
+      for (int k = 0; k < kCcPer + 2; ++k) {
+        const int t = t0 + k - 1;
+        fg[k] = (t >= 0 && t < tn) && (cls[(size_t)(pk[k] >> 16) * ld.w + (pk[k] & 0xFFFFu)] & kClassMask) == want;
+      }
+      int nstart = 0;
+      bool start[kCcPer], last[kCcPer];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      unsigned long long key = other[k];
+      for (int k = 1; k <= kCcPer; ++k) {
+        // the previous list entry is the left neighbour iff same row and x - 1 (packed values differ by one, x > 0)
+        const bool joined = fg[k] && fg[k - 1] && (pk[k] & 0xFFFFu) != 0u && pk[k - 1] + 1u == pk[k];
+        const bool joined_next = fg[k] && fg[k + 1] && (pk[k + 1] & 0xFFFFu) != 0u && pk[k] + 1u == pk[k + 1];
+        start[k - 1] = fg[k] && !joined;
+        last[k - 1] = fg[k] && !joined_next;
+        nstart += start[k - 1] ? 1 : 0;
+      }
+      int x = nstart;  // inclusive prefix of the run starts over the block
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        if (key > top[j]) {
-          const unsigned long long t = top[j];
-          top[j] = key;
-          key = t;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_warp[warp] = x;
+      __syncthreads();
+      int woff = 0, total = 0;
+#pragma unroll
+      for (int k = 0; k < kCcThreads / 32; ++k) {
+        const int v = s_warp[k];
+        woff += k < warp ? v : 0;
+        total += v;
+      }
+      int r = run0 + woff + x - nstart - 1;  // run of the entry in front of t0 (if it is foreground)
+#pragma unroll
+      for (int k = 0; k < kCcPer; ++k) {
+        const int t = t0 + k;
+        if (start[k]) {
+          ++r;
+          if (r < cap_runs) {
+            r_pk[r] = pk[k + 1];
+            r_parent[r] = r;
+            r_cnt[r] = 0;
+          }
         }
+        if (last[k] && r < cap_runs) r_x1[r] = (int)(pk[k + 1] & 0xFFFFu);
+        if (t < tn) ridx[t] = fg[k + 1] ? r : -1;
+      }
+      run0 += total;
+      __syncthreads();  // s_warp is reused by the next trip
     }
-  }
-  npix = __reduce_add_sync(0xffffffffu, npix);
-  ncomp = __reduce_add_sync(0xffffffffu, ncomp);
-  __shared__ unsigned long long stop[8 * 3];
-  __shared__ int snp[8], snc[8];
-  if (lane == 0) {
-    for (int k = 0; k < 3; ++k) stop[warp * 3 + k] = top[k];
-    snp[warp] = npix;
-    snc[warp] = ncomp;
+    nruns = run0;
+    if (nruns <= cap_runs) break;
+    r_pk = lw.run_pk + lbase;  // more runs than shared memory holds: the same tables in global memory
+    r_x1 = lw.run_x1 + lbase;
+    r_parent = lw.run_parent + lbase;
+    r_cnt = lw.run_cnt + lbase;
+    cap_runs = 0x7fffffff;
+    __syncthreads();
   }
   __syncthreads();
-  if (tid == 0) {
-    unsigned long long best[3] = {0ull, 0ull, 0ull};
-    int tp = 0, tc = 0;
-    for (int i = 0; i < 8; ++i) {
-      tp += snp[i];
-      tc += snc[i];
-      for (int k = 0; k < 3; ++k) {
-        unsigned long long key = stop[i * 3 + k];
-        if (key == 0ull) continue;
-        for (int j = 0; j < 3; ++j)
-          if (key > best[j]) {
-            const unsigned long long t = best[j];
-            best[j] = key;
-            key = t;
-          }
-      }
+  // 2. unions with the overlapping runs of the row above
+  for (int r = tid; r < nruns; r += kCcThreads) {
+    const uint32_t pk = r_pk[r];
+    const int y = pk >> 16, x0 = pk & 0xFFFFu, x1 = r_x1[r];
+    if (y == 0) continue;
+    const uint32_t key = ((uint32_t)(y - 1) << 16) | (uint32_t)x0;
+    int lo = 0, hi = r;  // first run (in front of r) that starts at or behind (y - 1, x0)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (r_pk[mid] < key) lo = mid + 1; else hi = mid;
     }
-    const int bg = ld.hw - tp;  // label 0 of this class's int image
-    const unsigned vbg = bg < ld.min_component ? 0u : (unsigned)bg;
-    unsigned long long key = ((unsigned long long)vbg << 32) | 0xFFFFFFFFull;  // label 0: wins every tie
-    for (int j = 0; j < 3; ++j)
-      if (key > best[j]) {
-        const unsigned long long t = best[j];
-        best[j] = key;
+    int j = lo;
+    if (j > 0 && (int)(r_pk[j - 1] >> 16) == y - 1) --j;  // the run that starts left of x0 may reach it
+    for (; j < r; ++j) {
+      const uint32_t pj = r_pk[j];
+      if ((int)(pj >> 16) != y - 1 || (int)(pj & 0xFFFFu) > x1) break;
+      if (r_x1[j] >= x0) uf_union(r_parent, r, j);
+    }
+  }
+  __syncthreads();
+  // 3. roots and component sizes
+  for (int r = tid; r < nruns; r += kCcThreads) {
+    const int root = uf_find(r_parent, r);
+    atomicAdd(&r_cnt[root], r_x1[r] - (int)(r_pk[r] & 0xFFFFu) + 1);
+  }
+  __syncthreads();
+  // 4. selection: entries are label 0 and the components; the component with the smaller root pixel has the smaller label
+  unsigned long long top[3] = {0ull, 0ull, 0ull};
+  int npix = 0, ncomp = 0;
+  for (int r = tid; r < nruns; r += kCcThreads) {
+    if (r_parent[r] != r) continue;
+    const int cnt = r_cnt[r];
+    npix += cnt;
+    ++ncomp;
+    const uint32_t pk = r_pk[r];
+    const int rp = (int)(pk >> 16) * ld.w + (int)(pk & 0xFFFFu);
+    const unsigned v = cnt < ld.min_component ? 0u : (unsigned)cnt;  // :66
+    unsigned long long key = ((unsigned long long)v << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)(rp + 1));
+    for (int k = 0; k < 3; ++k)
+      if (key > top[k]) {
+        const unsigned long long t = top[k];
+        top[k] = key;
         key = t;
       }
-    int sel = -1;                       // padding label: matches no pixel
-    if (ld.which < tc + 1) {            // real entries: label 0 and tc components
-      const unsigned long long k = best[ld.which];
-      const unsigned lab = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
-      sel = lab == 0u ? -2 : (int)lab - 1;
+  }
+  const int picked = cc_pick<kCcThreads / 32>(top, npix, ncomp, ld);
+  if (tid == 0) {
+    s_sel = picked;
+    lw.sel[job] = picked;
+  }
+  __syncthreads();
+  const int sel = s_sel;
+  // 5. component mask of every list entry (copy_components, :72-79)
+  for (int t = tid; t < tn; t += kCcThreads) {
+    const int r = ridx[t];
+    bool k = false;
+    if (sel == -2) {
+      k = r < 0;
+    } else if (sel >= 0 && r >= 0) {
+      const uint32_t pk = r_pk[uf_find(r_parent, r)];
+      k = (int)(pk >> 16) * ld.w + (int)(pk & 0xFFFFu) == sel;
     }
-    lw.sel[job] = sel;
+    keep[t] = k ? 1 : 0;
   }
 }
 
@@ -488,32 +685,42 @@ __global__ void __launch_bounds__(256) k_ls_reduce(WS ws, Dims d, LsWS lw, LsDim
 //                          go through the reference's float32 element-wise sequence (:89-108) into float64 sums.
 // Replaces k_gather_dirs + k_ls_weights + k_ls_reduce (102 us of launches and 140 MB of intermediates per 16 frames)
 // for the forward call; the backward pass still uses the gathered arrays.
+constexpr int kFusedTile = 512;  // list entries per tile of k_ls_fused (d.rtile of the forward call)
 __global__ void __launch_bounds__(512, 2) k_ls_fused(WS ws, Dims d, LsWS lw, LsDims ld, const float* __restrict__ seg,
-                                                  const float* __restrict__ direct, const float* __restrict__ conf) {
+                                                  const float* __restrict__ direct, const float* __restrict__ conf,
+                                                  int use_keep) {
   const int tid = threadIdx.x, lane = tid & 31, v = tid >> 5;
   const int n_rtiles = ws.rtile_start[d.J];
-  __shared__ float s_w[kRefineTile];
-  __shared__ uint32_t s_pix[kRefineTile];
-  __shared__ float2 s_c[kRefineTile];  // grid position (cy, cx) = ((y+.5)/H, (x+.5)/H): one pair of divisions per pixel
+  __shared__ float s_w[kFusedTile];
+  __shared__ uint32_t s_pix[kFusedTile];
+  __shared__ float2 s_c[kFusedTile];  // grid position (cy, cx) = ((y+.5)/H, (x+.5)/H): one pair of divisions per pixel
   const float fh = (float)ld.h;
   for (int rt = blockIdx.x; rt < n_rtiles; rt += gridDim.x) {
     const int job = ws.rtile_job[rt], tile = rt - ws.rtile_start[job];
     const int tn = ws.job_tn[job];
     const int img = job / d.oc, c = job - img * d.oc;
     const size_t base = (size_t)img * d.cap + ws.job_off[job];
-    const int sel = ld.filter ? lw.sel[job] : 0;
-    const int npx = min(kRefineTile, tn - tile * kRefineTile);
+    const int sel = (ld.filter && !use_keep) ? lw.sel[job] : 0;
+    const int npx = min(kFusedTile, tn - tile * kFusedTile);
     __syncthreads();  // the previous tile's readers are done with s_w / s_pix
     for (int k = tid; k < npx; k += blockDim.x) {
-      const uint32_t pk = ws.pix[base + (size_t)tile * kRefineTile + k];
+      const size_t le = base + (size_t)tile * kFusedTile + k;
+      const uint32_t pk = ws.pix[le];
+      const unsigned char kp = (ld.filter && use_keep) ? lw.keep[le] : (unsigned char)1;  // k_cc_runs' component mask
       const int x = pk & 0xFFFFu, y = pk >> 16;
       const size_t p = (size_t)img * ld.hw + (size_t)y * ld.w + x;
-      float row[33];
-      for (int q = 0; q < ld.nc; ++q) row[q] = __ldg(seg + p * ld.nc + q);
-      float w = hot_of_row(row, ld.nc, c + 1);  // hot_seg (:39-41)
+      const unsigned char c9raw = lw.cls9[p];
+      const int c9 = c9raw & kClassMask;
+      float w;
+      if (c9raw & kOneHotFlag) {  // exactly one-hot softmax (k_ls_classify): hot_seg is 1 for the pixel's class, else 0
+        w = c9 == c + 1 ? 1.0f : 0.0f;
+      } else {
+        float row[33];
+        for (int q = 0; q < ld.nc; ++q) row[q] = __ldg(seg + p * ld.nc + q);
+        w = hot_of_row(row, ld.nc, c + 1);  // hot_seg (:39-41)
+      }
       if (ld.filter) {                          // copy_components * hot_seg (:72-79)
-        const int c9 = lw.cls9[p];
-        const bool keep = sel == -2 ? (c9 != c + 1) : (sel >= 0 && c9 == c + 1 && lw.parent[p] == sel);
+        const bool keep = use_keep ? kp != 0 : (sel == -2 ? (c9 != c + 1) : (sel >= 0 && c9 == c + 1 && lw.parent[p] == sel));
         w = __fmul_rn(keep ? 1.0f : 0.0f, w);
       }
       s_w[k] = w;

@@ -33,6 +33,11 @@ def _run(Layer, seg, direct, conf, **kw):
     assert np.abs(sums - want).max() <= 1e-7 * scale, np.abs(sums - want).max() / scale
     err = float(np.abs(out.cpu().numpy() - ref).max())
     assert err <= TOL_PX, err
+    # the forward call proper (no debug outputs) finds the components over horizontal runs (k_cc_runs) instead of the
+    # pixel-level union-find the debug call keeps: same component mask, same tiles -> the same bits
+    fast = layer([torch.from_numpy(seg).cuda(), torch.from_numpy(direct).cuda(), torch.from_numpy(conf).cuda()])
+    torch.cuda.synchronize()
+    assert torch.equal(fast, out), float((fast - out).abs().max())
     return out, dbg, ref, rdbg
 
 
@@ -126,3 +131,21 @@ def test_tied_logits_list_a_pixel_for_every_class(Layer):
     g = torch.ones((b, nc - 1, vn, 2), device="cuda")
     gd, gw = layer.backward([torch.from_numpy(seg).cuda(), torch.from_numpy(direct).cuda(), torch.from_numpy(conf).cuda()], g)
     assert float(gd.abs().max()) > 0 and float(gw.abs().max()) > 0
+
+
+@pytest.mark.parametrize("second", [False, True])
+def test_salt_and_pepper_segmentation_has_more_runs_than_shared_memory_holds(Layer, second):
+    """A noisy segmentation (early in training): thousands of one- and two-pixel runs per class, far more than the
+    2048 runs k_cc_runs keeps in shared memory -> its global-memory run tables; components, selection and keypoints
+    must still be the oracle's (and the pixel-level union-find's)."""
+    rng = np.random.default_rng(5)
+    h, w, vn = 96, 128, 3
+    lab = rng.integers(0, 3, size=(h, w))
+    lab[20:50, 30:90] = 1  # one solid blob per class on top of the noise
+    lab[60:80, 10:60] = 2
+    seg = np.zeros((1, h, w, 3), np.float32)
+    for c in range(3):
+        seg[0, :, :, c] = np.where(lab == c, 3.0, 0.0)
+    direct = rng.normal(size=(1, h, w, 2 * vn)).astype(np.float32)
+    conf = rng.normal(size=(1, h, w, vn)).astype(np.float32)
+    _run(Layer, seg, direct, conf, filter_estimates=True, output_second_largest_component=second)

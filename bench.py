@@ -464,6 +464,8 @@ def main():
                 pending.wait()  # host-side check-point: the gathered keypoints of an earlier step are complete
             pending = nxt
         last = pending.wait()
+        if distributed:
+            last = last.clone()  # the gather buffers are reused by the next pass
         if mode >= 2:
             _lib.check(lib.casa_join(hdl, stream_ptr))  # the caller's stream waits for every lane
         e1.record()
@@ -541,7 +543,9 @@ def main():
         # the host entry splits the batch into image ranges (4 for b >= 8, 2 for b >= 2): even ranges cross PCIe as raw
         # floats, odd ranges as one host-packed u32 per pixel (casa_ransac_vote_host); CASA_NO_HOST_PACK=1 moves all raw
         parts = 4 if B >= 8 else (2 if B >= 2 else 1)
-        packed_imgs = 0 if os.environ.get("CASA_NO_HOST_PACK") else sum(
+        lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        pack_threads = min(8, ((os.cpu_count() or 1) - lws) // lws if lws > 1 else (os.cpu_count() or 1) - 1)  # the library's rule
+        packed_imgs = 0 if (os.environ.get("CASA_NO_HOST_PACK") or pack_threads < 4) else sum(
             B * (k + 1) // parts - B * k // parts for k in range(parts) if k & 1)
         px = h_ * w_
         moved_bytes = (B - packed_imgs) * px * oc * 4 + packed_imgs * px * 4 + float(mask_h.sum()) * 2 * vn * 4
@@ -552,7 +556,17 @@ def main():
 
     if rank == 0:
         sum_tn = float(mask_h.sum())
-        achieved = FLOP_PER_UNIT * units / (score_ms * 1e-3) / 1e12 if score_ms > 0 else None
+        # k_score of ROUND 0 of every step is event-timed (a WHILE body cannot hold event nodes).  For single-round frames
+        # the statistics' unit count is that launch's; for multi-round frames the units of round 0 are counted from the
+        # mask: every job with at least min_num pixels scores tn * vn * hn units (no figure if a job is above max_num,
+        # whose list is down-sampled at random).
+        tn_jobs = mask_h.sum(dim=(1, 2)).double()
+        units_round0 = float((tn_jobs * (tn_jobs >= 5)).sum()) * vn * hn * args.steps
+        multi_round = units > 1.0005 * units_round0
+        timed_units = units
+        if multi_round:
+            timed_units = None if bool((tn_jobs > 30000).any()) else units_round0
+        achieved = FLOP_PER_UNIT * timed_units / (score_ms * 1e-3) / 1e12 if (score_ms > 0 and timed_units) else None
         # frame-level roofline (frame-rate bound = 1 / (t_FP32 + t_HBM), no overlap assumed): algorithmic
         # FLOPs of all rounds at the measured FP32 peak + algorithmic bytes (read-once inputs, keypoints out) at the
         # measured HBM copy bandwidth, against the measured step
@@ -571,6 +585,7 @@ def main():
                 "workload": cfg["name"] % names,
                 "variant": args.variant, "masked_pixels_per_frame": sum_tn / B,
                 "units_per_step": units / max(args.steps, 1), "rounds_per_step": score_launches and units and None,
+                "units_round0_per_step": units_round0 / max(args.steps, 1),
                 "flop_per_unit": FLOP_PER_UNIT,
                 "l2": ("inputs (%.0f MB per step) larger than the 126 MB L2, no flush needed" % (in_bytes / 1e6)) if in_bytes > 126e6
                       else "inputs (%.0f MB per step) fit the 126 MB L2: k_score's operands are the compacted lists either way" % (in_bytes / 1e6),

@@ -1210,7 +1210,17 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   const bool vertex_mapped = !getenv("CASA_NO_ZERO_COPY") && host_pointer_is_mapped(vertex_host, &dv);
   const bool mask_mapped = host_pointer_is_mapped(mask_host, &dm);
   // host-side packing of the mask (any host memory: the CPU reads it) needs the vector field to be readable in place
-  const bool pack = vertex_mapped && !getenv("CASA_NO_HOST_PACK") && p->oc <= 32;
+  // host threads a rank may use for packing: one process per GPU (torchrun exports LOCAL_WORLD_SIZE) shares the node's
+  // cores with the other ranks; with fewer than 4 threads the DMA alone is faster (8 ranks on a 32-core host:
+  // profiles/r02_scale_n8*.json), so packing is switched off there
+  int pack_threads = (int)std::thread::hardware_concurrency() - 1;
+  {
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    if (lws && atoi(lws) > 1) pack_threads = ((int)std::thread::hardware_concurrency() - atoi(lws)) / atoi(lws);
+    if (getenv("CASA_HOST_THREADS")) pack_threads = atoi(getenv("CASA_HOST_THREADS"));
+    pack_threads = pack_threads > 8 ? 8 : pack_threads;  // more lose to oversubscription on a 16-core host
+  }
+  const bool pack = vertex_mapped && !getenv("CASA_NO_HOST_PACK") && p->oc <= 32 && (pack_threads >= 4 || !mask_mapped);
   const bool zero_copy = vertex_mapped && (pack || mask_mapped);
   const size_t bits_n = (size_t)p->b * hw * sizeof(uint32_t);
   const size_t bits_b = pack ? (bits_n + 255) & ~size_t(255) : 0;
@@ -1245,10 +1255,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     int pack_index[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (pack) {
       if (!h->packer) {
-        int n = (int)std::thread::hardware_concurrency() - 1;
-        if (getenv("CASA_HOST_THREADS")) n = atoi(getenv("CASA_HOST_THREADS"));
-        n = n < 1 ? 1 : (n > 8 ? 8 : n);  // more lose to oversubscription on a 16-core host
-        h->packer = new MaskPacker(n);
+        h->packer = new MaskPacker(pack_threads < 1 ? 1 : pack_threads);
       }
       if (h->bits_host_bytes < bits_n) {
         if (h->bits_host) CUDA_TRY(cudaFreeHost(h->bits_host));

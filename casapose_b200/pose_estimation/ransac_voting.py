@@ -122,6 +122,13 @@ def ransac_voting_layer_all_masks(
         rc = fn(
             hdl, C.byref(p), ptr(mask), ptr(vertex), ptr(idxs), ptr(selection), ptr(out),
             C.byref(dbg_struct) if dbg_struct is not None else None, current_stream_ptr(dev))
+        if rc == -3 and pix_capacity == 0 and not return_debug:
+            # CASA_ERR_WORKSPACE: channels that overlap list a pixel more than once and h*w slots per image are not
+            # enough.  The reference treats every channel independently (ransac_voting.py:458-470), so the call is
+            # repeated with room for every channel (synchronous calls only: an asynchronous one reports at casa_sync).
+            p.pix_capacity = oc * h * w
+            rc = fn(hdl, C.byref(p), ptr(mask), ptr(vertex), ptr(idxs), ptr(selection), ptr(out), None,
+                    current_stream_ptr(dev))
     _lib.check(rc)
     if return_debug:
         st = C.c_uint32()

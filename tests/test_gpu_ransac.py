@@ -219,11 +219,17 @@ def test_errors_are_reported_not_swallowed(vote):
         vote(m.double(), v, 16)
     with pytest.raises(ValueError):
         vote(m.cpu(), v, 16)
-    multi = torch.ones(1, 8, 8, 2, device="cuda")  # every pixel in both classes: 2*h*w entries > pix_capacity
+    multi = torch.ones(1, 8, 8, 2, device="cuda")  # every pixel in both classes: 2*h*w list entries per image
     with pytest.raises(CasaError):
-        vote(multi, v, 16)
+        vote(multi, v, 16, pix_capacity=64)  # an explicit capacity that is too small is an error
     out = vote(multi, v, 16, pix_capacity=2 * 64)  # enough room: runs
     assert out.shape == (1, 2, 9, 2)
+    # default capacity (h*w): the reference treats every channel independently and accepts overlapping channels
+    # (ransac_voting.py:458-470) — the synchronous call is repeated with room for every channel
+    rng = np.random.default_rng(3)
+    vv = torch.from_numpy(rng.normal(size=(1, 8, 8, 9, 2)).astype(np.float32)).cuda()
+    auto = vote(multi, vv, 16, seed=5)
+    assert torch.equal(auto, vote(multi, vv, 16, seed=5, pix_capacity=2 * 64))
 
 
 def test_host_buffer_entry_point_matches_device_path(vote):
@@ -277,3 +283,12 @@ def test_two_lane_mode_equals_the_synchronous_calls(vote, variant):
         assert torch.equal(e, g)
     again = vote(mask, vertex, 64, seed=seeds[0])
     assert torch.equal(again, expect[0])
+
+
+def test_overlapping_channels_vote_independently_like_the_reference(vote):
+    """Channels of `mask` need not be mutually exclusive in the reference (every channel is voted on by itself,
+    ransac_voting.py:458-470): a pixel in two channels is listed twice; counts, winners and keypoints are the oracle's."""
+    d = synthetic.make_frames(1, 64, 96, (1, 5), variant="easy")
+    mask = d["mask"].copy()
+    mask[0, :, :, 1] = np.maximum(mask[0, :, :, 1], mask[0, :, :, 0])  # channel 1 = union of both objects
+    _compare(vote, mask, d["vertex"], 64, seed=11, pix_capacity=2 * 64 * 96)

@@ -149,3 +149,27 @@ def test_salt_and_pepper_segmentation_has_more_runs_than_shared_memory_holds(Lay
     direct = rng.normal(size=(1, h, w, 2 * vn)).astype(np.float32)
     conf = rng.normal(size=(1, h, w, vn)).astype(np.float32)
     _run(Layer, seg, direct, conf, filter_estimates=True, output_second_largest_component=second)
+
+
+def test_ls_layer_with_three_calls_in_flight_equals_the_eager_calls(Layer):
+    """casa_set_async(h, 3): consecutive casa_ls_vote calls rotate over three lanes (own workspace, own stream); after
+    casa_join the results are the eager calls', bit for bit."""
+    from casapose_b200 import _lib
+
+    d = synthetic.make_frames(2, 120, 160, (1, 5, 6), variant="easy", with_logits=True)
+    seg = torch.from_numpy(d["seg_logits"]).cuda()
+    conf = torch.from_numpy(d["conf_logits"]).cuda()
+    directs = [torch.from_numpy(np.roll(d["vertex"].reshape(2, 120, 160, 18), k, axis=3).copy()).cuda() for k in range(5)]
+    layer = Layer("ls", seg.shape[3], num_points=9, filter_estimates=True)
+    expect = [layer([seg, x, conf]).clone() for x in directs]
+    torch.cuda.synchronize()
+    _lib.set_async(0, 3)
+    try:
+        outs = [layer([seg, x, conf], check_finite=False) for x in directs]
+        _lib.join(0)
+        got = [o.clone() for o in outs]
+        _lib.sync(0)
+    finally:
+        _lib.set_async(0, 0)
+    for e, g in zip(expect, got):
+        assert torch.equal(e, g)

@@ -207,7 +207,7 @@ struct casa_handle {
   uint64_t stats[4] = {0, 0, 0, 0};
   int64_t rounds_total = 0, launches_total = 0;
   unsigned long long* pinned_stats = nullptr;  // 4 words, page-locked
-  int score_occ = 0;
+  int score_occ = 0, score_occ_narrow = 0;  // resident k_score blocks per SM (8 / 4 hypotheses per lane)
   int fused_occ = 0;              // resident k_ls_fused blocks per SM (persistent grid of the LS forward call)
   int use_graph = 1;
   // keypoint all-gather (NCCL, resolved with dlopen: the library itself does not link against it)
@@ -937,12 +937,15 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
   sa.fc = fc;
   sa.one = 1u;
   if (h->score_occ == 0) {
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score, kScoreThreads, 0));
-    if (h->score_occ < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<kHypPerLaneWide>, kScoreThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ_narrow, k_score<kHypPerLaneNarrow>, kScoreThreads, 0));
+    if (h->score_occ < 1 || h->score_occ_narrow < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
     const char* bps = getenv("CASA_SCORE_BPS");  // cap on resident scoring blocks per SM (experiments)
     if (bps && atoi(bps) >= 1 && atoi(bps) < h->score_occ) h->score_occ = atoi(bps);
   }
-  const void* score_fn = (const void*)k_score;
+  const bool narrow = score_hpl(d.hn) == kHypPerLaneNarrow && !getenv("CASA_SCORE_WIDE");
+  const void* score_fn = narrow ? (const void*)k_score<kHypPerLaneNarrow> : (const void*)k_score<kHypPerLaneWide>;
+  const int score_occ = narrow ? h->score_occ_narrow : h->score_occ;
   const int refine_gx = d.max_rtiles < h->sm_count * 4 ? d.max_rtiles : h->sm_count * 4;
   const int gather_gx = (d.cap + 255) / 256 < 24 ? (d.cap + 255) / 256 : 24;
   const int vec4 = ((((size_t)d.hw * d.oc) & 3) == 0) && ((((uintptr_t)mask) & 15) == 0);
@@ -994,7 +997,7 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     // the timing events hang off the chain as leaves: ev0 fires when k_hypgen is done, ev1 when k_score is done
     if (part == 0 && h->timing) steps.push_back(special(STEP_EV0, 1));
     {
-      Step sc = kstep(score_fn, h->sm_count * h->score_occ, kScoreThreads).arg(sa);
+      Step sc = kstep(score_fn, h->sm_count * score_occ, kScoreThreads).arg(sa);
       if (part == 0) sc.joins(1);
       steps.push_back(sc);
     }

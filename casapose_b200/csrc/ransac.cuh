@@ -179,7 +179,8 @@ __device__ __forceinline__ unsigned prmt_sign2(float a, float b) {
 #ifndef CASA_PIX_UNROLL
 #define CASA_PIX_UNROLL 8
 #endif
-constexpr int kHypPerLane = CASA_HPL;             // hypotheses (and private counters) per lane of a scoring warp
+constexpr int kHypPerLaneWide = CASA_HPL;         // hypotheses (and private counters) per lane of a scoring warp
+constexpr int kHypPerLaneNarrow = 4;              // second instantiation for small hypothesis counts (see score_hpl())
 constexpr int kScoreMinBlocks = CASA_SCORE_MINB;  // resident 256-thread blocks per SM the kernel is compiled for
 constexpr int kPixUnroll = CASA_PIX_UNROLL;  // pixels per trip of the scoring loop
 
@@ -314,6 +315,10 @@ __device__ __forceinline__ int2 band_adjust2(const float4* __restrict__ cA, cons
 //  * min |t| per hypothesis pair is compared with B = c1 (|h'| + R): if min|t| >= B every sign in the
 //    chunk is provably the reference's verdict (predicate.cuh / DESIGN.md); otherwise band_adjust()
 //    finds the (rare) units that need the exact predicate.
+//  * a warp sweeps the hypotheses in groups of 32 * kHypPerLane; the kernel is instantiated for 8 (groups of 256) and
+//    for 4 hypotheses per lane (groups of 128: twice the shared-memory loads per unit, but a round of 128 hypotheses —
+//    BASELINE config 5's smallest sweep point — fills its group instead of half of it).
+template <int kHypPerLane>
 __global__ void __launch_bounds__(kScoreThreads, kScoreMinBlocks) k_score(ScoreArgs a) {
   __shared__ float4 sA[kScoreWarps][kChunk];  // (D, -E, -P0, A0)
   __shared__ float2 sB[kScoreWarps][kChunk];  // (-G, -H)
@@ -503,6 +508,10 @@ __global__ void __launch_bounds__(kScoreThreads, kScoreMinBlocks) k_score(ScoreA
     if (lane == 0 && n_flagged) atomicAdd(&a.ws.stats[3], (unsigned long long)n_flagged);
   }
 }
+
+// Hypotheses per lane for a round of hn hypotheses: the narrow instantiation when the last group of 256 would be at
+// most half full (hn mod 256 in 1..128), else the wide one.
+inline int score_hpl(int hn) { return ((hn - 1) % (32 * kHypPerLaneWide)) < 32 * kHypPerLaneNarrow ? kHypPerLaneNarrow : kHypPerLaneWide; }
 
 // ------------------------------------------------------------------------------------ stop test
 __device__ __forceinline__ double ipow_f64(double x, int n) {  // oracle/ransac_voting_np.py:_ipow_f64

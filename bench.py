@@ -556,13 +556,14 @@ def main():
             torch.cuda.synchronize()
             h2d_gbs = max(h2d_gbs, mask_h.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
         del scratch
-        # the host entry splits the batch into image ranges (4 for b >= 8, 2 for b >= 2): even ranges cross PCIe as raw
-        # floats, odd ranges as one host-packed u32 per pixel (casa_ransac_vote_host); CASA_NO_HOST_PACK=1 moves all raw
+        # the host entry splits the batch into image ranges (4 for b >= 8, 2 for b >= 2) whose masks cross PCIe as one
+        # host-packed u32 per pixel (6 or more host threads: every range; 4-5 threads: the odd ranges, the even ones as raw
+        # floats; fewer: raw floats only — casa_ransac_vote_host); CASA_NO_HOST_PACK=1 moves all raw
         parts = 4 if B >= 8 else (2 if B >= 2 else 1)
         lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-        pack_threads = min(8, ((os.cpu_count() or 1) - lws) // lws if lws > 1 else (os.cpu_count() or 1) - 1)  # the library's rule
-        packed_imgs = 0 if (os.environ.get("CASA_NO_HOST_PACK") or pack_threads < 4) else sum(
-            B * (k + 1) // parts - B * k // parts for k in range(parts) if k & 1)
+        pack_threads = min(12, ((os.cpu_count() or 1) - lws) // lws if lws > 1 else (os.cpu_count() or 1) - 1)  # the library's rule
+        packed_imgs = 0 if (os.environ.get("CASA_NO_HOST_PACK") or pack_threads < 4) else (B if pack_threads >= 6 else sum(
+            B * (k + 1) // parts - B * k // parts for k in range(parts) if k & 1))
         px = h_ * w_
         moved_bytes = (B - packed_imgs) * px * oc * 4 + packed_imgs * px * 4 + float(mask_h.sum()) * 2 * vn * 4
         e2e = {"value": n_images * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": in_bytes,

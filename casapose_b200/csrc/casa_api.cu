@@ -110,10 +110,31 @@ class MaskPacker {
   // bit c of bits[p] = (mask[p][c] != 0) — NaN counts as set, -0 does not, like tf.not_equal (:304); returns whether a
   // set element differs from 1.0 (CASA_STATUS_MASK_NOT_BINARY)
   __attribute__((target("avx2"))) static bool pack8_avx2(const float* mask, uint32_t* bits, size_t lo, size_t hi) {
-    // one 256-bit row per pixel: (v << 1) != 0 per lane -> 8-bit membership word; set lanes must hold 1.0f
+    // one 256-bit row per pixel: (v << 1) != 0 per lane -> 8-bit membership word; set lanes must hold 1.0f.  Eight rows
+    // per trip: their OR decides with one test whether all eight are background (87 % of the rows of an LM-O frame),
+    // which then cost eight loads and one 32-byte store (experimental/pack_bench.cpp: +45 % over the row-by-row loop).
     const __m256i zero = _mm256_setzero_si256(), one = _mm256_set1_epi32(0x3F800000);
     unsigned bad = 0;
-    for (size_t p = lo; p < hi; ++p) {
+    size_t p = lo;
+    for (; p + 8 <= hi; p += 8) {
+      const __m256i* r = reinterpret_cast<const __m256i*>(mask + 8 * p);
+      __m256i v[8];
+      for (int k = 0; k < 8; ++k) v[k] = _mm256_loadu_si256(r + k);
+      const __m256i any = _mm256_or_si256(_mm256_or_si256(_mm256_or_si256(v[0], v[1]), _mm256_or_si256(v[2], v[3])),
+                                          _mm256_or_si256(_mm256_or_si256(v[4], v[5]), _mm256_or_si256(v[6], v[7])));
+      if (_mm256_testz_si256(any, any)) {  // +0 everywhere (-0 and NaN have bits set and take the path below)
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(bits + p), zero);
+        continue;
+      }
+      for (int k = 0; k < 8; ++k) {
+        const unsigned z = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(_mm256_slli_epi32(v[k], 1), zero)));
+        const unsigned e1 = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(v[k], one)));
+        const unsigned m = ~z & 0xFFu;
+        bad |= m & ~e1;
+        bits[p + k] = m;
+      }
+    }
+    for (; p < hi; ++p) {
       const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(mask + 8 * p));
       const unsigned z = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(_mm256_slli_epi32(v, 1), zero)));
       const unsigned e1 = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(v, one)));
@@ -1221,7 +1242,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     const char* lws = getenv("LOCAL_WORLD_SIZE");
     if (lws && atoi(lws) > 1) pack_threads = ((int)std::thread::hardware_concurrency() - atoi(lws)) / atoi(lws);
     if (getenv("CASA_HOST_THREADS")) pack_threads = atoi(getenv("CASA_HOST_THREADS"));
-    pack_threads = pack_threads > 8 ? 8 : pack_threads;  // more lose to oversubscription on a 16-core host
+    pack_threads = pack_threads > 12 ? 12 : pack_threads;  // 15 of 16 cores lose to oversubscription (profiles/r02_e2e.txt)
   }
   const bool pack = vertex_mapped && !getenv("CASA_NO_HOST_PACK") && p->oc <= 32 && (pack_threads >= 4 || !mask_mapped);
   const bool zero_copy = vertex_mapped && (pack || mask_mapped);
@@ -1267,7 +1288,11 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
         CUDA_TRY(cudaHostAlloc((void**)&h->bits_host, bits_n, cudaHostAllocDefault));
         h->bits_host_bytes = bits_n;
       }
-      const bool all = getenv("CASA_HOST_PACK_ALL") != nullptr || !mask_mapped;  // a pageable mask cannot be DMA-copied in place
+      // With 6 or more host threads the packer (111 GB/s on the 16-core host of the pool, experimental/pack_bench.cpp)
+      // outruns the DMA of the raw floats: every range is packed and only 4 bytes per pixel cross PCIe (e2e 3.08 ms
+      // against 3.76 ms per 16 frames with half of the ranges packed: profiles/r02_e2e.txt).  With 4 or 5 threads the
+      // odd ranges are packed beside the DMA of the even ones.  A pageable mask cannot be DMA-copied in place.
+      const bool all = (pack_threads >= 6 && !getenv("CASA_HOST_PACK_HALF")) || getenv("CASA_HOST_PACK_ALL") != nullptr || !mask_mapped;
       std::vector<size_t> bounds;
       for (int k = 0; k < parts; ++k) {
         packed[k] = all || (k & 1);
@@ -1290,6 +1315,21 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     int64_t score_launches = 0;
     uint64_t stats[4] = {0, 0, 0, 0};
     uint32_t status = 0;
+    // The votes of the image ranges run on lanes (own workspace and stream each, casa_set_async(h, n)): the direction
+    // gather of one range (mapped reads over PCIe) and the short kernels of another overlap the scoring of a third,
+    // instead of four votes one behind the other on one stream.
+    const bool use_lanes = parts >= 2 && !getenv("CASA_HOST_NO_LANES");
+    if (use_lanes) {
+      for (int i = 0; i < kMaxLanes; ++i)  // lanes a caller left busy
+        if (h->lane[i] && h->lane_pending[i]) {
+          CUDA_TRY(cudaStreamSynchronize(h->lane[i]->own_stream));
+          h->lane_pending[i] = 0;
+        }
+      rc = collect(h);
+      if (rc) return rc;
+      reset_totals(h);
+      h->async_mode = parts < kMaxLanes ? parts : kMaxLanes;  // restored by async_off
+    }
     for (int k = 0; k < parts; ++k) {
       casa_ransac_params pp = *p;
       pp.b = start[k + 1] - start[k];
@@ -1314,11 +1354,26 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
             if (packed[j]) h->packer->wait_part((size_t)pack_index[j]);  // the workers still read the caller's buffer
         return rc;
       }
+      if (use_lanes) continue;  // collected below
       launches += h->last_launches;
       score_ms += h->score_ms;
       score_launches += h->score_launches;
       status |= h->last_status;
       for (int j = 0; j < 4; ++j) stats[j] += h->stats[j];
+    }
+    if (use_lanes) {
+      rc = casa_join(h, (void*)st);  // the result copy below waits for every lane
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      for (int i = 0; i < kMaxLanes; ++i) h->lane_pending[i] = 0;
+      rc = collect(h);  // loop states, statistics and the first error of the ranges' votes
+      h->last_launches = h->launches_total;
+      uint32_t st_all = 0;
+      for (int i = 0; i < kMaxLanes; ++i)
+        if (h->lane[i]) st_all |= h->lane[i]->last_status;
+      h->last_status = st_all;
+      return rc;
     }
     h->last_launches = launches;
     h->score_ms = score_ms;

@@ -575,14 +575,13 @@ def main():
         sum_tn = float(mask_h.sum())
         # k_score of ROUND 0 of every step is event-timed (a WHILE body cannot hold event nodes).  For single-round frames
         # the statistics' unit count is that launch's; for multi-round frames the units of round 0 are counted from the
-        # mask: every job with at least min_num pixels scores tn * vn * hn units (no figure if a job is above max_num,
-        # whose list is down-sampled at random).
+        # mask: every job with at least min_num pixels scores tn * vn * hn units (a job above max_num: its expected
+        # max_num pixels after the random down-sampling).
         tn_jobs = mask_h.sum(dim=(1, 2)).double()
-        units_round0 = float((tn_jobs * (tn_jobs >= 5)).sum()) * vn * hn * args.steps
-        multi_round = units > 1.0005 * units_round0
-        timed_units = units
-        if multi_round:
-            timed_units = None if bool((tn_jobs > 30000).any()) else units_round0
+        tn_round0 = torch.clamp(tn_jobs, max=30000.0) * (tn_jobs >= 5)  # a job above max_num keeps max_num pixels on average (:298)
+        units_round0 = float(tn_round0.sum()) * vn * hn * args.steps
+        multi_round = units > 1.001 * units_round0
+        timed_units = units_round0 if multi_round else units
         achieved = FLOP_PER_UNIT * timed_units / (score_ms * 1e-3) / 1e12 if (score_ms > 0 and timed_units) else None
         # frame-level roofline (frame-rate bound = 1 / (t_FP32 + t_HBM), no overlap assumed): algorithmic
         # FLOPs of all rounds at the measured FP32 peak + algorithmic bytes (read-once inputs, keypoints out) at the

@@ -828,7 +828,7 @@ __device__ __forceinline__ void pinv2x2_apply(double a, double b, double c, doub
 // one warp per job, lane v = keypoint
 __global__ void __launch_bounds__(32) k_ls_solve(WS ws, Dims d, LsDims ld, float* __restrict__ out, double* dbg_sums, uint32_t* sticky) {
   const int job = blockIdx.x, v = threadIdx.x;
-  if (job == 0 && v == 0 && sticky) {  // a pixel-list overflow (raised by k_job_tables) must not stay silent: -> casa_sync
+  if (job == 0 && v == 0 && sticky) {  // a pixel-list overflow (raised by k_place) must not stay silent: -> casa_sync
     const unsigned st = (unsigned)ws.ctrl[CTRL_STATUS] & CASA_STATUS_PIX_OVERFLOW;
     if (st) atomicOr(sticky, st);
   }

@@ -40,7 +40,27 @@ poses = pnp_cuda(torch.from_numpy(uv).cuda(), kp3, cams, np.tile(np.array([0, 0,
 counts = np.array([700, 3417, 9], np.int32)
 pts = (rng.uniform(-0.5, 0.5, size=(3, 3417, 3)) * 80).astype(np.float32)
 rows = pose_errors_cuda(poses, RT, cams, pts, counts, np.full(3, 100.0, np.float32), np.array([1, 1, 0], np.int32), 5.0)
+# round 2: lanes (three votes / LS calls in flight, joined on the caller's stream), the run-based components with more
+# runs than shared memory holds, overlapping mask channels (call repeated with room for every channel)
+from casapose_b200 import _lib  # noqa: E402
+
+_lib.set_async(0, 3)
+lane_outs = [ransac_voting_layer_all_masks(m, v, 64, seed=s, max_iter=3) for s in (1, 2, 3, 4)]
+lane_ls = [layer([seg_t, dir_t, conf_t], check_finite=False) for _ in range(3)]
+_lib.join(0)
+_lib.sync(0)
+_lib.set_async(0, 0)
+assert torch.equal(lane_outs[0], out) and torch.equal(lane_ls[0], ls)
+noise = rng.integers(0, 3, size=(96, 128))
+seg_n = np.zeros((1, 96, 128, 3), np.float32)
+for c in range(3):
+    seg_n[0, :, :, c] = np.where(noise == c, 3.0, 0.0)
+ls_noise = CoordLSVotingWeighted("ls3", 3, num_points=9, filter_estimates=True)(
+    [torch.from_numpy(seg_n).cuda(), dir_t[:1].contiguous(), conf_t[:1].contiguous()])
+multi = np.maximum(d["mask"], d["mask"][..., ::-1].copy())  # every channel also holds another one's pixels
+out5 = ransac_voting_layer_all_masks(torch.from_numpy(multi).cuda(), v, 32, seed=1, max_iter=2)
 torch.cuda.synchronize()
+assert torch.isfinite(ls_noise).all() and torch.isfinite(out5).all()
 assert torch.isfinite(gd).all() and torch.isfinite(gw).all() and torch.isfinite(rows).all() and torch.isfinite(ls_plain).all()
 assert torch.equal(out.cpu(), host)
 print("sanitize run ok", float(out.abs().sum()), float(ls.abs().sum()))

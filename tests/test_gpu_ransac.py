@@ -292,3 +292,36 @@ def test_overlapping_channels_vote_independently_like_the_reference(vote):
     mask = d["mask"].copy()
     mask[0, :, :, 1] = np.maximum(mask[0, :, :, 1], mask[0, :, :, 0])  # channel 1 = union of both objects
     _compare(vote, mask, d["vertex"], 64, seed=11, pix_capacity=2 * 64 * 96)
+
+
+def test_lanes_with_changing_shapes_and_a_failing_call(vote):
+    """Lane mode with calls of different shapes (each lane keeps its own graphs and workspace), and a call whose pixel
+    lists overflow: the error surfaces at casa_sync (asynchronous calls cannot repeat themselves), the other calls'
+    results are the eager ones, and the handle works on afterwards."""
+    from casapose_b200 import _lib
+    from casapose_b200._lib import CasaError
+
+    frames = [synthetic.make_frames(b, hh, ww, ids, variant="easy", seed=3 + b)
+              for b, hh, ww, ids in ((1, 64, 96, (1, 5)), (2, 96, 128, synthetic.CONFIG_8_IDS), (3, 48, 64, (6,)), (1, 96, 128, (1, 5, 6)))]
+    ins = [(torch.from_numpy(d["mask"]).cuda(), torch.from_numpy(d["vertex"]).cuda()) for d in frames]
+    expect = [vote(m, v, 64, seed=2).clone() for m, v in ins]
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.set_async(0, 3, stream)
+    try:
+        outs = [vote(m, v, 64, seed=2) for m, v in ins + ins]
+        _lib.join(0, stream)
+        got = [o.clone() for o in outs]
+        _lib.sync(0, stream)
+        for k, g in enumerate(got):
+            assert torch.equal(expect[k % len(ins)], g), k
+        multi = torch.ones(1, 8, 8, 2, device="cuda")  # every pixel in both channels: 2*h*w entries > h*w slots
+        vote(multi, torch.zeros(1, 8, 8, 9, 2, device="cuda"), 16)
+        ok = vote(ins[0][0], ins[0][1], 64, seed=2)
+        with pytest.raises(CasaError):
+            _lib.sync(0, stream)
+        assert torch.equal(ok, expect[0])
+        _lib.sync(0, stream)  # the error was reported once
+    finally:
+        _lib.set_async(0, 0, stream)
+    assert torch.equal(vote(ins[1][0], ins[1][1], 64, seed=2), expect[1])

@@ -11,7 +11,9 @@ ranks are all-gathered with NCCL inside the timed step).
 
   value    frames/s, inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
   e2e      frames/s through the host-buffer C-ABI entry point (pinned host -> device copy of mask and
-           vertex field, voting, device -> host copy of the keypoints, all inside the timed region)
+           vertex field, voting, device -> host copy of the keypoints, all inside the timed region), two calls in
+           flight (casa_ransac_vote_host_async; every call's keypoints are waited for inside the timed region);
+           e2e.one_call_at_a_time is the synchronous call, one behind the other
   roofline the scoring kernel k_score against the FP32 FMA issue rate measured in this same run
            (FFMA micro-kernel of the library); algorithmic work = 11 FLOP per (hypothesis, pixel,
            keypoint) test
@@ -50,6 +52,9 @@ def parse():
                     help="BASELINE.json config: 2 (default, the headline), 3 (13 objects, batch 32), 4 (batch 256 sharded: strong scaling), 5 (1080x1920, --hn sweep)")
     ap.add_argument("--hn", type=int, default=None, help="hypotheses per round (config 5 sweep: 128 .. 2048)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-calls", type=int, default=2,
+                    help="host-buffer calls in flight in the e2e pass (1: synchronous casa_ransac_vote_host; "
+                         "2: casa_ransac_vote_host_async, the default)")
     ap.add_argument("--lanes", type=int, default=3, help="calls in flight in the timed region (casa_set_async); 1 = one lane")
     ap.add_argument("--variant", default="easy")
     ap.add_argument("--cpu-sample-frames", type=int, default=None,
@@ -530,20 +535,43 @@ def main():
     # --- end to end through the host-buffer C-ABI entry point (pinned host buffers)
     e2e = None
     if not args.no_e2e:
-        out_h = torch.empty((B, oc, vn, 2), dtype=torch.float32).pin_memory()
         e2e_steps = max(3, min(args.steps, int(2.0e10 / max(in_bytes, 1))))  # about 20 GB over PCIe at most
-        for it in range(2):
-            ransac_voting_layer_all_masks_host(mask_h, vertex_h, hn, seed=it, image_offset=start_img, device=local, out=out_h)
-        barrier()
-        t0 = time.perf_counter()
-        for it in range(e2e_steps):
-            ransac_voting_layer_all_masks_host(mask_h, vertex_h, hn, seed=2000 + it, image_offset=start_img, device=local, out=out_h)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        if distributed:
-            t = torch.tensor([e2e_s], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        outs_h = [torch.empty((B, oc, vn, 2), dtype=torch.float32).pin_memory() for _ in range(args.host_calls + 1)]
+
+        def e2e_pass(in_flight):
+            """e2e_steps host-buffer calls, `in_flight` of them at a time (1: the synchronous call; 2: the pipelined
+            entry, casa_ransac_vote_host_async — the host packs call i+1 while the GPU finishes call i).  Every call's
+            keypoints are waited for inside the timed region; they land in pinned host memory."""
+            from collections import deque
+
+            for it in range(2 * in_flight):
+                ransac_voting_layer_all_masks_host(mask_h, vertex_h, hn, seed=it, image_offset=start_img, device=local,
+                                                   out=outs_h[0], wait=in_flight == 1)
+            _lib.sync(local)
+            barrier()
+            pend = deque()
+            t0 = time.perf_counter()
+            for it in range(e2e_steps):
+                if in_flight == 1:
+                    ransac_voting_layer_all_masks_host(mask_h, vertex_h, hn, seed=2000 + it, image_offset=start_img, device=local,
+                                                       out=outs_h[0])
+                    continue
+                if len(pend) == in_flight:
+                    pend.popleft().result()
+                pend.append(ransac_voting_layer_all_masks_host(mask_h, vertex_h, hn, seed=2000 + it, image_offset=start_img,
+                                                               device=local, out=outs_h[it % len(outs_h)], wait=False))
+            while pend:
+                pend.popleft().result()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if distributed:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+
+        e2e_one_s = e2e_pass(1)
+        e2e_s = e2e_pass(args.host_calls) if args.host_calls > 1 else e2e_one_s
         # context for e2e: pinned host -> device copy bandwidth of this box, and the bytes the host entry point really
         # moves (the whole mask by DMA, the vector field only at masked pixels through mapped reads)
         scratch = torch.empty_like(mask)
@@ -569,7 +597,9 @@ def main():
         e2e = {"value": n_images * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
                "d2h_bytes_per_step": B * oc * vn * 2 * 4, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
                "h2d_gbs_measured": h2d_gbs, "bytes_moved_per_step": moved_bytes, "host_packed_images": packed_imgs,
-               "pcie_floor_ms": moved_bytes / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None}
+               "pcie_floor_ms": moved_bytes / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None,
+               "host_calls_in_flight": args.host_calls,
+               "one_call_at_a_time": {"value": n_images * e2e_steps / e2e_one_s, "ms_per_step": e2e_one_s / e2e_steps * 1e3}}
 
     if rank == 0:
         sum_tn = float(mask_h.sum())

@@ -261,6 +261,16 @@ struct casa_handle {
   uint32_t* sticky = nullptr;     // device word: OR of the status words of every call since the last casa_sync
   uint32_t* pinned_sticky = nullptr;
   std::vector<struct casa_graph*> graphs;
+  // Pipelined host entry (casa_ransac_vote_host_async): kHostDepth driver threads, each with a sub-handle of its own
+  // (workspaces, lanes, staging buffers), run casa_ransac_vote_host for consecutive tickets; they share this handle's
+  // packer threads behind `pack_gate`, so the host packs call i+1 while the GPU finishes call i.
+  struct HostDriver* driver[4] = {nullptr, nullptr, nullptr, nullptr};
+  int host_depth = 0;             // drivers in use (fixed at the first asynchronous call)
+  int64_t host_ticket = 0;        // tickets issued
+  int host_first_rc = 0;          // first error of a call whose ticket was never waited for
+  char host_first_err[512] = "";
+  casa_handle* host_parent = nullptr;  // set in a driver's sub-handle: owner of the shared packer
+  std::mutex pack_gate;           // one call at a time uses the packer threads
 };
 
 struct casa_graph {
@@ -367,9 +377,13 @@ extern "C" int casa_create(int device, casa_handle** out) {
   return CASA_OK;
 }
 
+static void host_drivers_destroy(casa_handle* h);
+static int host_drain(casa_handle* h);
+
 extern "C" int casa_destroy(casa_handle* h) {
   if (!h) return CASA_OK;
   cudaSetDevice(h->device);
+  host_drivers_destroy(h);  // pipelined host calls: wait for them, stop the driver threads
   for (casa_graph* g : h->graphs) {
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
@@ -1277,9 +1291,16 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     uint32_t* dbits = (uint32_t*)((char*)h->io_mem + mask_b - bits_b);
     bool packed[9] = {false, false, false, false, false, false, false, false, false};
     int pack_index[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // pipelined calls (casa_ransac_vote_host_async) share the parent handle's packer threads: the gate is held from the
+    // start of this call's packing until its last range is packed, then the next call's packing starts while this
+    // call's last ranges are still being voted on
+    casa_handle* po = h->host_parent ? h->host_parent : h;
+    std::unique_lock<std::mutex> gate;
+    int last_packed = -1;
     if (pack) {
-      if (!h->packer) {
-        h->packer = new MaskPacker(pack_threads < 1 ? 1 : pack_threads);
+      if (h->host_parent || h->host_depth) gate = std::unique_lock<std::mutex>(po->pack_gate);
+      if (!po->packer) {
+        po->packer = new MaskPacker(pack_threads < 1 ? 1 : pack_threads);
       }
       if (h->bits_host_bytes < bits_n) {
         if (h->bits_host) CUDA_TRY(cudaFreeHost(h->bits_host));
@@ -1297,12 +1318,13 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       for (int k = 0; k < parts; ++k) {
         packed[k] = all || (k & 1);
         if (packed[k]) {
+          last_packed = k;
           pack_index[k] = (int)bounds.size() / 2;
           bounds.push_back((size_t)start[k] * hw);
           bounds.push_back((size_t)start[k + 1] * hw);
         }
       }
-      h->packer->start(mask_host, h->bits_host, p->oc, bounds);
+      po->packer->start(mask_host, h->bits_host, p->oc, bounds);
     }
     for (int k = 0; k < parts; ++k) {  // the raw ranges are queued up front on the copy stream
       if (packed[k]) continue;
@@ -1335,11 +1357,12 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       pp.b = start[k + 1] - start[k];
       pp.image_offset = p->image_offset + start[k];
       if (packed[k]) {
-        h->packer->wait_part((size_t)pack_index[k]);
+        po->packer->wait_part((size_t)pack_index[k]);
+        h->host_not_binary = po->packer->not_binary();
+        if (k == last_packed && gate.owns_lock()) gate.unlock();  // the packer threads are free for the next call
         const size_t o = (size_t)start[k] * hw, n = (size_t)pp.b * hw;
         CUDA_TRY(cudaMemcpyAsync(dbits + o, h->bits_host + o, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->copy_stream));
         CUDA_TRY(cudaEventRecord(h->part_ev[k], h->copy_stream));
-        h->host_not_binary = h->packer->not_binary();
       }
       CUDA_TRY(cudaStreamWaitEvent(st, h->part_ev[k], 0));
       if (packed[k])
@@ -1351,7 +1374,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       if (rc) {
         if (pack)
           for (int j = k + 1; j < parts; ++j)
-            if (packed[j]) h->packer->wait_part((size_t)pack_index[j]);  // the workers still read the caller's buffer
+            if (packed[j]) po->packer->wait_part((size_t)pack_index[j]);  // the workers still read the caller's buffer
         return rc;
       }
       if (use_lanes) continue;  // collected below
@@ -1383,6 +1406,168 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   }
   CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return CASA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pipelined host entry
+// casa_ransac_vote_host is synchronous like the reference's call: it returns with the keypoints on the host, and its
+// phases run one behind the other — the host threads pack the mask (about 60 % of the call), then the GPU finishes the
+// last image ranges while the host threads idle.  A caller that streams batches (an evaluation loop over a data set)
+// can keep kHostDepth calls in flight instead: casa_ransac_vote_host_async hands the call to a driver thread with a
+// sub-handle of its own and returns a ticket, casa_host_wait(ticket) returns that call's error code once its keypoints
+// are in out_points_host.  The drivers share the packer threads (one call packs at a time, in ticket order for two
+// drivers), so call i+1 is packed while the GPU votes on the last ranges of call i.
+struct HostJob {
+  casa_ransac_params p;
+  const float* mask = nullptr;
+  const float* vertex = nullptr;
+  float* out = nullptr;
+  int64_t ticket = -1;
+  int rc = 0;
+  uint32_t status = 0;
+  int64_t launches = 0;
+  char err[512] = "";
+};
+
+struct HostDriver {
+  casa_handle* sub = nullptr;
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  int state = 0;  // 0 idle, 1 queued / running, 2 done and not yet collected
+  bool quit = false;
+  HostJob job;
+};
+
+static void host_driver_run(HostDriver* d) {
+  for (;;) {
+    std::unique_lock<std::mutex> g(d->m);
+    d->cv.wait(g, [&] { return d->quit || d->state == 1; });
+    if (d->quit) return;
+    const HostJob j = d->job;
+    g.unlock();
+    const int rc = casa_ransac_vote_host(d->sub, &j.p, j.mask, j.vertex, j.out);
+    g.lock();
+    d->job.rc = rc;
+    d->job.status = d->sub->last_status;
+    d->job.launches = d->sub->last_launches;
+    if (rc) snprintf(d->job.err, sizeof(d->job.err), "%s", g_err);  // this thread's last error
+    d->state = 2;
+    d->cv.notify_all();
+  }
+}
+
+// keeps the first error of a finished call nobody waited for (reported by the next casa_host_wait / casa_sync)
+static void host_fold(casa_handle* h, HostDriver* d) {
+  if (d->state != 2) return;
+  if (d->job.rc && !h->host_first_rc) {
+    h->host_first_rc = d->job.rc;
+    snprintf(h->host_first_err, sizeof(h->host_first_err), "%s", d->job.err);
+  }
+  h->last_status = d->job.status;
+  h->last_launches = d->job.launches;
+  d->state = 0;
+}
+
+static void host_drivers_destroy(casa_handle* h) {
+  for (int i = 0; i < 4; ++i) {
+    HostDriver* d = h->driver[i];
+    if (!d) continue;
+    {
+      std::unique_lock<std::mutex> g(d->m);
+      d->cv.wait(g, [&] { return d->state != 1; });
+      d->quit = true;
+    }
+    d->cv.notify_all();
+    if (d->th.joinable()) d->th.join();
+    if (d->sub) casa_destroy(d->sub);
+    delete d;
+    h->driver[i] = nullptr;
+  }
+}
+
+// waits for every call in flight; returns the first error among the calls that were not waited for by ticket
+static int host_drain(casa_handle* h) {
+  for (int i = 0; i < 4; ++i) {
+    HostDriver* d = h->driver[i];
+    if (!d) continue;
+    std::unique_lock<std::mutex> g(d->m);
+    d->cv.wait(g, [&] { return d->state != 1; });
+    host_fold(h, d);
+  }
+  if (h->host_first_rc) {
+    const int rc = h->host_first_rc;
+    h->host_first_rc = 0;
+    return fail(rc, "%s", h->host_first_err);
+  }
+  return CASA_OK;
+}
+
+extern "C" int casa_ransac_vote_host_async(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
+                                           const float* vertex_host, float* out_points_host, int64_t* ticket) {
+  if (!h || !p || !ticket) return fail(CASA_ERR_INVALID, "handle / params / ticket is NULL");
+  if (!mask_host || !vertex_host || !out_points_host) return fail(CASA_ERR_INVALID, "host buffers must not be NULL");
+  if (h->host_parent || h->is_lane) return fail(CASA_ERR_INVALID, "casa_ransac_vote_host_async: not on a sub-handle");
+  {
+    Layout L;  // shape errors are the caller's at once, not the driver thread's later
+    const int rcl = make_layout(p, L);
+    if (rcl) return rcl;
+  }
+  if (!h->host_depth) {
+    int depth = 2;
+    if (getenv("CASA_HOST_DEPTH")) depth = atoi(getenv("CASA_HOST_DEPTH"));
+    h->host_depth = depth < 1 ? 1 : (depth > 4 ? 4 : depth);
+  }
+  const int k = (int)(h->host_ticket % h->host_depth);
+  if (!h->driver[k]) {
+    casa_handle* sub = nullptr;
+    const int rcc = casa_create(h->device, &sub);
+    if (rcc) return rcc;
+    sub->host_parent = h;
+    HostDriver* d = new HostDriver();
+    d->sub = sub;
+    d->th = std::thread(host_driver_run, d);
+    h->driver[k] = d;
+  }
+  HostDriver* d = h->driver[k];
+  {
+    std::unique_lock<std::mutex> g(d->m);
+    d->cv.wait(g, [&] { return d->state != 1; });  // the call `depth` tickets ago still runs
+    host_fold(h, d);
+    d->job = HostJob();
+    d->job.p = *p;
+    d->job.mask = mask_host;
+    d->job.vertex = vertex_host;
+    d->job.out = out_points_host;
+    d->job.ticket = h->host_ticket;
+    d->state = 1;
+  }
+  d->cv.notify_all();
+  *ticket = h->host_ticket++;
+  return CASA_OK;
+}
+
+extern "C" int casa_host_wait(casa_handle* h, int64_t ticket) {
+  if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
+  if (ticket < 0 || ticket >= h->host_ticket || !h->host_depth) return fail(CASA_ERR_INVALID, "casa_host_wait: unknown ticket %lld", (long long)ticket);
+  HostDriver* d = h->driver[ticket % h->host_depth];
+  std::unique_lock<std::mutex> g(d->m);
+  if (d->job.ticket == ticket && d->state != 0) {
+    d->cv.wait(g, [&] { return d->state == 2; });
+    const int rc = d->job.rc;
+    h->last_status = d->job.status;
+    h->last_launches = d->job.launches;
+    d->state = 0;
+    if (rc) return fail(rc, "%s", d->job.err);
+    return CASA_OK;
+  }
+  g.unlock();
+  // collected before (waited twice, or overtaken by a later call on its driver): report a kept error once
+  if (h->host_first_rc) {
+    const int rc = h->host_first_rc;
+    h->host_first_rc = 0;
+    return fail(rc, "%s", h->host_first_err);
+  }
   return CASA_OK;
 }
 
@@ -1676,6 +1861,8 @@ extern "C" int casa_join(casa_handle* h, void* stream) {
 extern "C" int casa_sync(casa_handle* h) {
   if (!h) return fail(CASA_ERR_INVALID, "NULL argument");
   CUDA_TRY(cudaSetDevice(h->device));
+  const int rch = host_drain(h);  // pipelined host calls in flight (casa_ransac_vote_host_async)
+  if (rch) return rch;
   int rc = collect(h);
   CUDA_TRY(cudaStreamSynchronize(h->last_stream));
   if (h->deferred_list) run_deferred(h, true);

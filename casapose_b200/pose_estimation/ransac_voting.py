@@ -138,10 +138,39 @@ def ransac_voting_layer_all_masks(
     return out
 
 
+class PendingHostVote:
+    """A host-buffer vote in flight (ransac_voting_layer_all_masks_host(..., wait=False)).  result() blocks until the
+    keypoints are in the output tensor and returns it (raises what the synchronous call would have raised); the
+    object keeps the input and output buffers alive until then."""
+
+    def __init__(self, hdl, ticket, out, keep):
+        self._hdl, self._ticket, self._out, self._keep, self._done = hdl, ticket, out, keep, False
+
+    def result(self):
+        if not self._done:
+            self._done = True
+            rc = _lib.lib().casa_host_wait(self._hdl, self._ticket)
+            self._keep = None
+            _lib.check(rc)
+        return self._out
+
+    def __del__(self):  # the library reads the buffers until the call is done
+        if not self._done:
+            try:
+                self._done = True
+                _lib.lib().casa_host_wait(self._hdl, self._ticket)
+            except Exception:
+                pass
+
+
 def ransac_voting_layer_all_masks_host(mask, vertex, round_hyp_num, inlier_thresh=0.99, confidence=0.99, max_iter=20,
-                                       min_num=5, max_num=30000, *, seed=0, image_offset=0, device=0, out=None):
+                                       min_num=5, max_num=30000, *, seed=0, image_offset=0, device=0, out=None, wait=True):
     """Same call with HOST tensors (numpy arrays or CPU torch tensors, ideally pinned): host->device copy,
-    voting, device->host copy of the [b,oc,vn,2] result — all inside the library (casa_ransac_vote_host)."""
+    voting, device->host copy of the [b,oc,vn,2] result — all inside the library (casa_ransac_vote_host).
+
+    wait=False (casa_ransac_vote_host_async) returns a PendingHostVote at once; up to two such calls run at a time,
+    the host packing of one beside the GPU work of the other, and a third call blocks until the oldest has finished.
+    The input buffers must not be modified before result() has returned."""
     mask_t = torch.as_tensor(mask)
     vertex_t = torch.as_tensor(vertex)
     if mask_t.is_cuda or vertex_t.is_cuda:
@@ -173,6 +202,11 @@ def ransac_voting_layer_all_masks_host(mask, vertex, round_hyp_num, inlier_thres
                 or tuple(out.shape) != (b, oc, vn, 2):
             raise ValueError("out must be a contiguous CPU float32 tensor [b,oc,vn,2] = %s" % ((b, oc, vn, 2),))
     hdl = _lib.handle(device)
+    if not wait:
+        ticket = C.c_int64(-1)
+        _lib.check(_lib.lib().casa_ransac_vote_host_async(hdl, C.byref(p), mask_t.data_ptr(), vertex_t.data_ptr(),
+                                                          out.data_ptr(), C.byref(ticket)))
+        return PendingHostVote(hdl, ticket.value, out, (mask_t, vertex_t))
     rc = _lib.lib().casa_ransac_vote_host(hdl, C.byref(p), mask_t.data_ptr(), vertex_t.data_ptr(), out.data_ptr())
     _lib.check(rc)
     return out

@@ -141,6 +141,22 @@ int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const flo
                           const float* vertex_host, float* out_points_host);
 
 /*
+ * The host-buffer call with several calls in flight, for callers that stream batches — the evaluation loop of
+ * /root/reference/test_casapose.py:439-443 calls ransac_voting_layer_all_masks (pose_evaluation.py:50-58) once
+ * per batch and looks at the keypoints afterwards.  casa_ransac_vote_host_async hands the call to a driver
+ * thread of the handle and returns a ticket at once; casa_host_wait(ticket) blocks until that call's keypoints
+ * are in out_points_host and returns its error code (casa_last_error() holds its message).  Two calls run at a
+ * time (CASA_HOST_DEPTH=1..4): the host threads pack the mask of call i+1 while the GPU votes on the last image
+ * ranges of call i.  A third call waits inside casa_ransac_vote_host_async for the oldest one.  The buffers of
+ * a call must stay valid and untouched until its ticket has been waited for; results are bit-identical to
+ * casa_ransac_vote_host.  casa_sync() waits for every call in flight and reports the first error of a call
+ * nobody waited for.
+ */
+int casa_ransac_vote_host_async(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
+                                const float* vertex_host, float* out_points_host, int64_t* ticket);
+int casa_host_wait(casa_handle* h, int64_t ticket);
+
+/*
  * CoordLSVotingWeighted(name, num_classes, num_points, sigmoid_weights, filter_estimates,
  * output_second_largest_component)([seg, direct, w])
  * (/root/reference/casapose/pose_estimation/voting_layers_2d.py:5-122).

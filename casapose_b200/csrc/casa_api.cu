@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -1216,6 +1217,19 @@ static bool host_pointer_is_mapped(const void* p, const void** dev_ptr) {
   return true;
 }
 
+// CASA_HOST_TRACE=1: host-side time stamps of the phases of casa_ransac_vote_host on stderr (microseconds)
+static double host_now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static bool host_trace_on() {
+  static const bool on = getenv("CASA_HOST_TRACE") != nullptr;
+  return on;
+}
+#define HOST_TRACE(h, what, k) \
+  do {                         \
+    if (host_trace_on()) fprintf(stderr, "[host %p] %12.1f %s %d\n", (void*)(h), host_now_us(), what, (int)(k)); \
+  } while (0)
+
 extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
                                      const float* vertex_host, float* out_points_host) {
   if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
@@ -1298,7 +1312,9 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     std::unique_lock<std::mutex> gate;
     int last_packed = -1;
     if (pack) {
+      HOST_TRACE(h, "enter", 0);
       if (h->host_parent || h->host_depth) gate = std::unique_lock<std::mutex>(po->pack_gate);
+      HOST_TRACE(h, "gate", 0);
       if (!po->packer) {
         po->packer = new MaskPacker(pack_threads < 1 ? 1 : pack_threads);
       }
@@ -1358,6 +1374,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       pp.image_offset = p->image_offset + start[k];
       if (packed[k]) {
         po->packer->wait_part((size_t)pack_index[k]);
+        HOST_TRACE(h, "packed", k);
         h->host_not_binary = po->packer->not_binary();
         if (k == last_packed && gate.owns_lock()) gate.unlock();  // the packer threads are free for the next call
         const size_t o = (size_t)start[k] * hw, n = (size_t)pp.b * hw;
@@ -1371,6 +1388,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       else
         rc = casa_ransac_vote(h, &pp, dmask + (size_t)start[k] * mask_img, (const float*)dv + (size_t)start[k] * vert_img,
                               nullptr, nullptr, dout + (size_t)start[k] * out_img, nullptr, (void*)st);
+      HOST_TRACE(h, "issued", k);
       if (rc) {
         if (pack)
           for (int j = k + 1; j < parts; ++j)
@@ -1389,6 +1407,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       if (rc) return rc;
       CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
+      HOST_TRACE(h, "done", 0);
       for (int i = 0; i < kMaxLanes; ++i) h->lane_pending[i] = 0;
       rc = collect(h);  // loop states, statistics and the first error of the ranges' votes
       h->last_launches = h->launches_total;

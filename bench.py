@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--host-calls", type=int, default=2,
                     help="host-buffer calls in flight in the e2e pass (1: synchronous casa_ransac_vote_host; "
                          "2: casa_ransac_vote_host_async, the default)")
-    ap.add_argument("--lanes", type=int, default=3, help="calls in flight in the timed region (casa_set_async); 1 = one lane")
+    ap.add_argument("--lanes", type=int, default=4, help="calls in flight in the timed region (casa_set_async); 1 = one lane")
     ap.add_argument("--variant", default="easy")
     ap.add_argument("--cpu-sample-frames", type=int, default=None,
                     help="frames of the batch the CPU restatement is timed on (default: 8 for the cpu_baseline leg = about 8 s, 1 per step for --impl reference)")

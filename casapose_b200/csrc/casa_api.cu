@@ -976,8 +976,13 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<kHypPerLaneWide>, kScoreThreads, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ_narrow, k_score<kHypPerLaneNarrow>, kScoreThreads, 0));
     if (h->score_occ < 1 || h->score_occ_narrow < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
-    const char* bps = getenv("CASA_SCORE_BPS");  // cap on resident scoring blocks per SM (experiments)
-    if (bps && atoi(bps) >= 1 && atoi(bps) < h->score_occ) h->score_occ = atoi(bps);
+    // Votes on lanes leave one of the four block slots of every SM to the neighbouring votes' short kernels: the scoring
+    // kernel keeps its rate at three (and two) resident blocks, and the step is 1-2 % shorter (profiles/r02_lanes_overlap.txt).
+    int cap = h->is_lane ? 3 : h->score_occ;
+    const char* bps = getenv("CASA_SCORE_BPS");  // experiments
+    if (bps && atoi(bps) >= 1) cap = atoi(bps);
+    if (cap < h->score_occ) h->score_occ = cap;
+    if (cap < h->score_occ_narrow) h->score_occ_narrow = cap;
   }
   const bool narrow = score_hpl(d.hn) == kHypPerLaneNarrow && !getenv("CASA_SCORE_WIDE");
   const void* score_fn = narrow ? (const void*)k_score<kHypPerLaneNarrow> : (const void*)k_score<kHypPerLaneWide>;

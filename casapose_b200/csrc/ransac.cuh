@@ -29,7 +29,8 @@ __device__ __forceinline__ const float2* job_dirs(const WS& ws, const Dims& d, i
 }
 
 // ------------------------------------------------------------------------------------ K2
-// grid (ceil(hn*vn/256), J): one thread per (hypothesis, keypoint) of an active job
+// grid (ceil(hn*vn/256), J): one thread per (keypoint, hypothesis) of an active job, hypotheses fastest — the three
+// [J][vn][hn] outputs are written in full lines (hypothesis-fastest threads wrote them with a stride of hn entries)
 __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, const int32_t* __restrict__ idxs, int rnd,
                                                 float* dbg_hyps) {
   const int job = blockIdx.y;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) k_hypgen(WS ws, Dims d, FilterConsts fc, 
   const int tn = ws.job_tn[job];
   const int img = job / d.oc, cls = job - img * d.oc;
   const uint32_t* pix = ws.pix + (size_t)img * d.cap + ws.job_off[job];
-  const int h = e / d.vn, v = e - h * d.vn;
+  const int v = e / d.hn, h = e - v * d.hn;
   const float2* vd = job_dirs(ws, d, img, job, tn, v);
   int2 ip;
   if (idxs) {

@@ -59,6 +59,11 @@ ls_noise = CoordLSVotingWeighted("ls3", 3, num_points=9, filter_estimates=True)(
     [torch.from_numpy(seg_n).cuda(), dir_t[:1].contiguous(), conf_t[:1].contiguous()])
 multi = np.maximum(d["mask"], d["mask"][..., ::-1].copy())  # every channel also holds another one's pixels
 out5 = ransac_voting_layer_all_masks(torch.from_numpy(multi).cuda(), v, 32, seed=1, max_iter=2)
+# session 3 of round 2: the pipelined host entry (driver threads, shared packer: three calls queued, two in flight)
+mh, vh = torch.from_numpy(d["mask"]).pin_memory(), torch.from_numpy(d["vertex"]).pin_memory()
+pend = [ransac_voting_layer_all_masks_host(mh, vh, 64, seed=1, max_iter=3, wait=False) for _ in range(3)]
+for pnd in pend:
+    assert torch.equal(pnd.result(), host)
 torch.cuda.synchronize()
 assert torch.isfinite(ls_noise).all() and torch.isfinite(out5).all()
 assert torch.isfinite(gd).all() and torch.isfinite(gw).all() and torch.isfinite(rows).all() and torch.isfinite(ls_plain).all()

@@ -57,3 +57,16 @@ def test_product_path_fails_loudly_without_cuda(cuda_lib):
 
     with pytest.raises(ValueError):
         ransac_voting_layer_all_masks(torch.zeros(1, 8, 8, 2), torch.zeros(1, 8, 8, 9, 2), 16)
+
+
+def test_pipelined_host_entry_rejects_bad_arguments_without_gpu(cuda_lib):
+    """casa_ransac_vote_host_async / casa_host_wait validate their arguments before touching a device."""
+    from casapose_b200 import _lib
+
+    ticket = C.c_int64(-1)
+    p = _lib.RansacParams(b=1, h=8, w=8, oc=2, vn=9, round_hyp_num=16, max_iter=2, inlier_thresh=0.99, confidence=0.99,
+                          min_num=5, max_num=30000)
+    assert cuda_lib.casa_ransac_vote_host_async(None, C.byref(p), None, None, None, C.byref(ticket)) == -1
+    assert b"NULL" in cuda_lib.casa_last_error()
+    assert cuda_lib.casa_host_wait(None, 0) == -1
+    assert ticket.value == -1

@@ -193,7 +193,7 @@ def run_ls(args):
         # mode >= 2: that many calls in flight (casa_set_async: consecutive calls rotate over workspaces / streams, so the
         # latency-bound classify / place / component kernels of neighbouring calls overlap); 1: one call at a time
         _lib.set_async(0, mode)
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(args.warmup, 3, 2 * mode)):  # at least two untimed steps per lane (workspace, graph)
             layer([seg, direct, conf], check_finite=False)
         _lib.join(0)
         torch.cuda.synchronize()
@@ -444,7 +444,8 @@ def main():
     def timed_pass(mode, timing, sample, own_sampler=None):
         _lib.check(lib.casa_set_async(hdl, mode))
         _lib.check(lib.casa_set_timing(hdl, 0))
-        for it in range(max(args.warmup, 3)):
+        # at least two untimed steps per lane: a lane builds its workspace and its graph on its first call
+        for it in range(max(args.warmup, 3, 2 * mode)):
             step(it).wait()
         if mode >= 2:
             _lib.check(lib.casa_join(hdl, stream_ptr))

@@ -976,8 +976,9 @@ static int ransac_vote_impl(casa_handle* h, const casa_ransac_params* p, const f
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ, k_score<kHypPerLaneWide>, kScoreThreads, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->score_occ_narrow, k_score<kHypPerLaneNarrow>, kScoreThreads, 0));
     if (h->score_occ < 1 || h->score_occ_narrow < 1) return fail(CASA_ERR_INVALID, "scoring kernel does not fit");
-    // Votes on lanes leave one of the four block slots of every SM to the neighbouring votes' short kernels: the scoring
-    // kernel keeps its rate at three (and two) resident blocks, and the step is 1-2 % shorter (profiles/r02_lanes_overlap.txt).
+    // The kernel is compiled for two resident blocks per SM (113 registers: ransac.cuh).  With the four-block build of
+    // the first half of round 2 (CASA_SCORE_MINB=4) votes on lanes ran three blocks per SM and left the fourth slot to
+    // the neighbouring votes' short kernels (1-2 % per step: profiles/r02_lanes_overlap.txt).
     int cap = h->is_lane ? 3 : h->score_occ;
     const char* bps = getenv("CASA_SCORE_BPS");  // experiments
     if (bps && atoi(bps) >= 1) cap = atoi(bps);

@@ -168,14 +168,18 @@ __device__ __forceinline__ unsigned prmt_sign2(float a, float b) {
 
 // Build-time knobs of k_score, chosen by same-box A/B runs (profiles/r02_ab.txt).  The kernel is bound by dispatch
 // cycles, and the register allocation ptxas finds for the 440-instruction loop body moves the result by +-2 %:
-//   hypotheses per lane 8 (16: 128 registers, 2 blocks/SM, -8 %), 4 resident blocks/SM at 64 registers (3 at 80: -1 %),
-//   8 pixels per trip (4: -1 %, 2: spills at 64 registers), binary search over item_start (a 16-byte record per chunk
-//   removed the search but cost 2-4 % through a worse allocation of the loop).
+//   hypotheses per lane 8 (16: 128 registers, -8..-13 %), TWO resident blocks/SM at 113 registers (the kernel keeps its
+//   rate down to two blocks per SM — it is bound by issue slots, not occupancy — and without the 64-register squeeze
+//   ptxas finds a schedule of the same 434-instruction loop that runs 2.2 % faster: 0.709 against 0.726 ms; 4 blocks at
+//   64 registers was the form of the first half of round 2, 3 at 80: -2 %; register caps of 72..120 through
+//   __maxnreg__ or a larger launch-bounds thread count: all slower, 0.723..0.783 ms), 8 pixels per trip (16: the same,
+//   4: -1 %), binary search over item_start (a 16-byte record per chunk removed the search but cost 2-4 % through a
+//   worse allocation of the loop).
 #ifndef CASA_HPL
 #define CASA_HPL 8
 #endif
 #ifndef CASA_SCORE_MINB
-#define CASA_SCORE_MINB 4
+#define CASA_SCORE_MINB 2
 #endif
 #ifndef CASA_PIX_UNROLL
 #define CASA_PIX_UNROLL 8

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -60,51 +61,69 @@ class MaskPacker {
     cv_.notify_all();
     for (std::thread& t : workers_) t.join();
   }
-  // packs `mask` ([npx][oc] floats) into `bits`; part k = pixels [bounds[2k], bounds[2k+1]), parts in order
+  // packs `mask` ([npx][oc] floats) into `bits`; part k = pixels [bounds[2k], bounds[2k+1]), parts in order.
+  // The workers take kChunkPx-pixel chunks of the current part from a shared counter, and a part is done when its
+  // last chunk is — not when every worker has reported — so a worker the host has descheduled (the caller's driver
+  // threads, the Python thread and the CUDA runtime share the cores) holds up one chunk, not the part.
   void start(const float* mask, uint32_t* bits, int oc, const std::vector<size_t>& bounds) {
+    std::shared_ptr<Job> j = std::make_shared<Job>();
+    j->mask = mask;
+    j->bits = bits;
+    j->oc = oc;
+    j->bounds = bounds;
+    const size_t parts = bounds.size() / 2;
+    j->nchunks.resize(parts);
+    j->next.reset(new std::atomic<size_t>[parts ? parts : 1]);
+    j->done.reset(new std::atomic<size_t>[parts ? parts : 1]);
+    for (size_t k = 0; k < parts; ++k) {
+      j->nchunks[k] = (bounds[2 * k + 1] - bounds[2 * k] + kChunkPx - 1) / kChunkPx;
+      j->next[k].store(0);
+      j->done[k].store(0);
+    }
     std::lock_guard<std::mutex> g(m_);
-    mask_ = mask;
-    bits_ = bits;
-    oc_ = oc;
-    bounds_ = bounds;
-    done_.assign(bounds.size() / 2, 0);
-    not_binary_.store(0);
+    job_ = j;
     ++epoch_;
     cv_.notify_all();
   }
   void wait_part(size_t k) {
     std::unique_lock<std::mutex> g(m_);
-    cv_done_.wait(g, [&] { return done_[k] == n_; });
+    cv_done_.wait(g, [&] { return job_->done[k].load() >= job_->nchunks[k]; });
   }
-  int not_binary() const { return not_binary_.load(); }
+  int not_binary() const { return job_ ? job_->not_binary.load() : 0; }
 
  private:
-  void run(int id) {
+  static constexpr size_t kChunkPx = 8192;  // 256 KB of an 8-channel mask per chunk
+  struct Job {  // one start(): a straggler of the previous call keeps its own (exhausted) job
+    const float* mask = nullptr;
+    uint32_t* bits = nullptr;
+    int oc = 0;
+    std::vector<size_t> bounds, nchunks;
+    std::unique_ptr<std::atomic<size_t>[]> next, done;
+    std::atomic<int> not_binary{0};
+  };
+  void run(int) {
     long long seen = 0;
     for (;;) {
-      std::vector<size_t> bounds;
-      const float* mask;
-      uint32_t* bits;
-      int oc;
+      std::shared_ptr<Job> j;
       {
         std::unique_lock<std::mutex> g(m_);
         cv_.wait(g, [&] { return quit_ || epoch_ != seen; });
         if (quit_) return;
         seen = epoch_;
-        bounds = bounds_;
-        mask = mask_;
-        bits = bits_;
-        oc = oc_;
+        j = job_;
       }
-      for (size_t k = 0; 2 * k + 1 < bounds.size(); ++k) {  // every worker takes its slice of every part, parts in order
-        const size_t n = bounds[2 * k + 1] - bounds[2 * k];
-        const size_t lo = bounds[2 * k] + n * id / n_, hi = bounds[2 * k] + n * (id + 1) / n_;
-        if (pack(mask, bits, oc, lo, hi)) not_binary_.store(1);
-        {
-          std::lock_guard<std::mutex> g(m_);
-          ++done_[k];
+      for (size_t k = 0; k < j->nchunks.size(); ++k) {  // parts in order, chunks of a part from the shared counter
+        const size_t lo0 = j->bounds[2 * k], hi0 = j->bounds[2 * k + 1];
+        for (;;) {
+          const size_t c = j->next[k].fetch_add(1);
+          if (c >= j->nchunks[k]) break;
+          const size_t lo = lo0 + c * kChunkPx, hi = lo + kChunkPx < hi0 ? lo + kChunkPx : hi0;
+          if (pack(j->mask, j->bits, j->oc, lo, hi)) j->not_binary.store(1);
+          if (j->done[k].fetch_add(1) + 1 == j->nchunks[k]) {
+            std::lock_guard<std::mutex> g(m_);
+            cv_done_.notify_all();
+          }
         }
-        cv_done_.notify_all();
       }
     }
   }
@@ -187,12 +206,7 @@ class MaskPacker {
   std::condition_variable cv_, cv_done_;
   bool quit_ = false;
   long long epoch_ = 0;
-  const float* mask_ = nullptr;
-  uint32_t* bits_ = nullptr;
-  int oc_ = 0;
-  std::vector<size_t> bounds_;
-  std::vector<int> done_;
-  std::atomic<int> not_binary_{0};
+  std::shared_ptr<Job> job_;
 };
 }  // namespace
 
@@ -271,6 +285,8 @@ struct casa_handle {
   int host_first_rc = 0;          // first error of a call whose ticket was never waited for
   char host_first_err[512] = "";
   casa_handle* host_parent = nullptr;  // set in a driver's sub-handle: owner of the shared packer
+  cudaEvent_t ev_block = nullptr;      // driver sub-handles: blocking-sync event (a waiting driver thread sleeps instead of
+                                       // spinning on a core the packer threads need)
   std::mutex pack_gate;           // one call at a time uses the packer threads
 };
 
@@ -422,6 +438,7 @@ extern "C" int casa_destroy(casa_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_round) cudaEventDestroy(h->ev_round);
+  if (h->ev_block) cudaEventDestroy(h->ev_block);
   for (int i = 0; i < kCallSlots; ++i) {
     if (h->slots[i].ev0) cudaEventDestroy(h->slots[i].ev0);
     if (h->slots[i].ev1) cudaEventDestroy(h->slots[i].ev1);
@@ -1236,6 +1253,19 @@ static bool host_trace_on() {
     if (host_trace_on()) fprintf(stderr, "[host %p] %12.1f %s %d\n", (void*)(h), host_now_us(), what, (int)(k)); \
   } while (0)
 
+// Waits for `st`.  The driver threads of the pipelined host entry sleep on a blocking-sync event: a spinning
+// cudaStreamSynchronize would take a core from the packer threads for the two milliseconds of a call's GPU tail.
+static int host_wait_stream(casa_handle* h, cudaStream_t st) {
+  if (h->host_parent && !getenv("CASA_HOST_SPIN")) {
+    if (!h->ev_block) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(h->ev_block, st));
+    CUDA_TRY(cudaEventSynchronize(h->ev_block));
+    return CASA_OK;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return CASA_OK;
+}
+
 extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p, const float* mask_host,
                                      const float* vertex_host, float* out_points_host) {
   if (!h || !p) return fail(CASA_ERR_INVALID, "handle / params is NULL");
@@ -1412,7 +1442,8 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
       rc = casa_join(h, (void*)st);  // the result copy below waits for every lane
       if (rc) return rc;
       CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
+      rc = host_wait_stream(h, st);
+      if (rc) return rc;
       HOST_TRACE(h, "done", 0);
       for (int i = 0; i < kMaxLanes; ++i) h->lane_pending[i] = 0;
       rc = collect(h);  // loop states, statistics and the first error of the ranges' votes
@@ -1430,8 +1461,7 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
     for (int j = 0; j < 4; ++j) h->stats[j] = stats[j];
   }
   CUDA_TRY(cudaMemcpyAsync(out_points_host, dout, out_b, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  return CASA_OK;
+  return host_wait_stream(h, st);
 }
 
 // ------------------------------------------------------------------------------------------------ pipelined host entry

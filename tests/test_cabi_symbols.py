@@ -70,3 +70,18 @@ def test_pipelined_host_entry_rejects_bad_arguments_without_gpu(cuda_lib):
     assert b"NULL" in cuda_lib.casa_last_error()
     assert cuda_lib.casa_host_wait(None, 0) == -1
     assert ticket.value == -1
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/casapose_b200.h compiles as C99 with warnings on (plain pointers and sizes,
+    no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "casapose_b200.h"\nint main(void) { return casa_version() == 0; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr

@@ -97,6 +97,7 @@ EXPORTS = {
     "casa_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "casa_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "casa_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]),
+    "casa_selftest_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "casa_selftest_filter": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_float,
                                        C.POINTER(C.c_uint64)]),
     "casa_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -1464,6 +1464,21 @@ extern "C" int casa_ransac_vote_host(casa_handle* h, const casa_ransac_params* p
   return host_wait_stream(h, st);
 }
 
+extern "C" int casa_selftest_pack(const float* mask, uint32_t* bits, int64_t npx, int oc, int threads, int parts) {
+  if (!mask || !bits) return fail(CASA_ERR_INVALID, "casa_selftest_pack: NULL buffer");
+  if (npx < 0 || oc < 1 || oc > 32 || threads < 1 || threads > 64 || parts < 1 || parts > 8)
+    return fail(CASA_ERR_INVALID, "casa_selftest_pack: npx=%lld oc=%d threads=%d parts=%d", (long long)npx, oc, threads, parts);
+  MaskPacker packer(threads);
+  std::vector<size_t> bounds;
+  for (int k = 0; k < parts; ++k) {
+    bounds.push_back((size_t)(npx * k / parts));
+    bounds.push_back((size_t)(npx * (k + 1) / parts));
+  }
+  packer.start(mask, bits, oc, bounds);
+  for (int k = 0; k < parts; ++k) packer.wait_part((size_t)k);
+  return packer.not_binary();
+}
+
 // ------------------------------------------------------------------------------------------------ pipelined host entry
 // casa_ransac_vote_host is synchronous like the reference's call: it returns with the keypoints on the host, and its
 // phases run one behind the other — the host threads pack the mask (about 60 % of the call), then the GPU finishes the

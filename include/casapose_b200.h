@@ -326,6 +326,14 @@ int casa_set_timing(casa_handle* h, int enable);
 int casa_get_timing(casa_handle* h, double* score_ms, int64_t* score_launches, uint64_t* stats4);
 
 /*
+ * Test hook of the host mask packer casa_ransac_vote_host uses (no device involved): packs mask [npx][oc] float32
+ * into one membership word per pixel, bit c = (mask[p][c] != 0) as tf.not_equal counts it (ransac_voting.py:304:
+ * NaN is set, -0 is not), on `threads` host threads in `parts` consecutive ranges.  Returns 1 if a set element
+ * differs from 1.0 (what the vote reports as CASA_STATUS_MASK_NOT_BINARY), 0 if not, a negative error code otherwise.
+ */
+int casa_selftest_pack(const float* mask, uint32_t* bits, int64_t npx, int oc, int threads, int parts);
+
+/*
  * Self-test of the filtered inlier predicate: draws n adversarial (pixel, hypothesis)
  * pairs concentrated on the decision boundary and compares filter+fallback with the
  * reference-exact float32 sequence (ransac_voting.py:230-249).
